@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — MoL brute-force top-k queries/s (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (north star): synthetic MoL 8x8x32 (d=32, D=64, H=128, tau=0.05), top-100 over a 1M-item
+corpus, batch of 512 queries per step.  A "step" is one MoLBruteForceTopK.forward over the batch.
+With N>1 the corpus is sharded by contiguous item range over the ranks (strong scaling), each rank
+searches its shard, and one NCCL all-gather + a GPU merge produce the global top-k on every rank.
+
+One JSON line on rank 0:  value = whole-job queries/s with inputs resident in HBM; e2e = the same
+through the C-ABI host entry (pinned host queries in, scores/ids out, copies inside the timed region);
+roofline = the dominant scoring kernel against MEASURED_PEAKS.json; cpu_baseline = the CPU oracle
+(port of the reference's PyTorch path) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "MoL brute-force top-k queries/sec over N-item corpus"
+UNIT = "queries/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--items", type=int, default=1_000_000)
+    p.add_argument("--batch", type=int, default=512)
+    p.add_argument("--k", type=int, default=100)
+    p.add_argument("--mode", default="auto", choices=["auto", "exact", "tensor"])
+    p.add_argument("--cpu-queries", type=int, default=8, help="queries in the cpu_baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def workload_cfg():
+    from oracle.mol_oracle import MoLConfig
+
+    return MoLConfig(64, 64, 32, 8, 8, 0.05, "geglu", ())
+
+
+def workload_name(args):
+    return (
+        f"synthetic MoL 8x8x32 d=32 D=64 H=128, top-{args.k} over {args.items} items, batch={args.batch}"
+    )
+
+
+def flops_per_pair(cfg):
+    L = cfg.num_logits
+    return 2 * L * cfg.dot_product_dimension + 4 * L * 128  # F = 2*L*d + 4*L*H
+
+
+def bytes_per_item(cfg):
+    return 2 * (cfg.item_dot_product_groups * cfg.dot_product_dimension + cfg.num_logits)  # bf16 X_sub + GI
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons during the timed region (nvidia-smi's clocks line via NVML)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+        s = sorted(self.samples)
+        return {
+            "sm_mhz": s[len(s) // 2] if s else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(s),
+        }
+
+
+def cpu_oracle_time(cfg, sd, items_cpu, ids_cpu, queries_cpu, k, reps=1):
+    """Times the CPU oracle (oracle/mol_oracle.py, the port of the reference's PyTorch path) with all host threads."""
+    from oracle import mol_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    best = None
+    with torch.inference_mode():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.brute_force_top_k(cfg, sd, queries_cpu, items_cpu, ids_cpu, k, chunk=2)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return best
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port: the reference
+    is pure PyTorch and /root/reference does not exist on the GPU box), all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload_cfg()
+    from tests.helpers import build_module, synthetic_inputs
+
+    mol, _ = build_module(cfg, None, "cpu", seed=0)
+    sd = {k: v.detach() for k, v in mol.state_dict().items()}
+    nq = 2
+    items, ids, q, _ = synthetic_inputs(cfg, args.items, nq, 0, "cpu")
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    for _ in range(warm):
+        cpu_oracle_time(cfg, sd, items, ids, q, args.k)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_oracle_time(cfg, sd, items, ids, q, args.k)
+    dt = (time.perf_counter() - t0) / steps
+    qps = nq / dt
+    cores = torch.get_num_threads()
+    sample = f"{nq} queries x full {args.items}-item corpus per step (chunks of 2 queries), fp32, eager"
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": sample},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    from rails_b200 import _lib, engine
+    from rails_b200.indexing.mol_top_k import MoLBruteForceTopK
+    from tests.helpers import build_module
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        print("bench.py: --gpus N>1 must be launched with torch.distributed.run", file=sys.stderr)
+        sys.exit(2)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    mode = {"auto": _lib.MODE_AUTO, "exact": _lib.MODE_EXACT, "tensor": _lib.MODE_TENSOR}[args.mode]
+
+    cfg = workload_cfg()
+    B, k, N = args.batch, args.k, args.items
+    mol, _ = build_module(cfg, None, dev, seed=0)
+    # corpus shard of this rank: contiguous item range, generated on device
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    items = 0.02 * torch.randn(hi - lo, cfg.item_embedding_dim, device=dev, generator=g)
+    ids = torch.arange(lo + 1, hi + 1, dtype=torch.int64, device=dev)
+    gq = torch.Generator().manual_seed(100)
+    q_host = F.layer_norm(torch.randn(B, cfg.query_embedding_dim, generator=gq), (cfg.query_embedding_dim,)).pin_memory()
+    q_dev = q_host.to(dev)
+    top = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=mode)
+    index = top._ensure_index()
+    weights = mol.packed_weights(dev)
+    wsp = mol.workspace(dev)
+    out_s_host = torch.empty((B, k), dtype=torch.float32).pin_memory()
+    out_i_host = torch.empty((B, k), dtype=torch.int64).pin_memory()
+    tensor_path = engine.tensor_path_supported(weights.shape) and mode != _lib.MODE_EXACT
+
+    if world > 1:
+        gather_s = torch.empty((world, B, k), dtype=torch.float32, device=dev)
+        gather_i = torch.empty((world, B, k), dtype=torch.int64, device=dev)
+
+    def step_device():
+        s, i = engine.search(weights, index, wsp, q_dev, None, k, True, mode)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_s, s)
+            dist.all_gather_into_tensor(gather_i, i)
+            s, i = engine.merge_topk(gather_s, gather_i, k)
+        return s, i
+
+    def step_e2e():
+        if world == 1:
+            engine.search_host(weights, index, wsp, q_host, None, k, out_s_host, out_i_host, mode)
+        else:
+            qd = q_host.to(dev, non_blocking=True)
+            s, i = engine.search(weights, index, wsp, qd, None, k, True, mode)
+            dist.all_gather_into_tensor(gather_s, s)
+            dist.all_gather_into_tensor(gather_i, i)
+            s, i = engine.merge_topk(gather_s, gather_i, k)
+            out_s_host.copy_(s, non_blocking=True)
+            out_i_host.copy_(i, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.mol_launch_count_reset()
+    lib.mol_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = int(lib.mol_launch_count())
+    import ctypes
+
+    k_ms, k_n = ctypes.c_double(), ctypes.c_int32()
+    _lib.check(lib.mol_profile_collect(ctypes.byref(k_ms), ctypes.byref(k_n)))
+    lib.mol_profile_enable(0)
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = B / (ms_step * 1e-3)
+
+    # ---- end to end through the host entry (pinned host buffers, copies inside the timed region)
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e = {
+        "value": B / (ms_e2e * 1e-3), "unit": UNIT,
+        "h2d_bytes_per_step": q_host.numel() * 4,
+        "d2h_bytes_per_step": out_s_host.numel() * 4 + out_i_host.numel() * 8,
+        "ms_per_step": ms_e2e,
+    }
+
+    # ---- roofline of the dominant kernel (scoring pass), this rank's shard
+    tf_peak, hbm_peak, peak_src = peaks()
+    n_local = hi - lo
+    kern_ms = k_ms.value / max(k_n.value, 1)
+    queries_per_launch = B * args.steps / max(k_n.value, 1)
+    flops_launch = queries_per_launch * n_local * flops_per_pair(cfg)
+    achieved_tf = flops_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+    if not tensor_path:
+        tf_peak_used, peak_note = tf_peak, peak_src + "; NOTE fp32 CUDA-core kernel measured against the tensor roofline"
+    else:
+        tf_peak_used, peak_note = tf_peak, peak_src
+    roofline = {
+        "bound": "tensor", "kernel": "mol_coarse_tcgen05" if tensor_path else "exact_scores_kernel(fp32)",
+        "achieved": achieved_tf, "peak": tf_peak_used, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak_used,
+        "traffic": None, "peak_source": peak_note,
+        "kernel_ms_per_launch": kern_ms, "kernel_share_of_step": (k_ms.value / args.steps) / ms_step,
+        "hbm_gbs_algorithmic": (n_local * bytes_per_item(cfg)) / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0,
+        "hbm_peak_gbs": hbm_peak,
+    }
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sd = {kk: v.detach().cpu() for kk, v in mol.state_dict().items()}
+        nq = args.cpu_queries
+        t = cpu_oracle_time(cfg, sd, items.cpu(), ids.cpu(), q_host[:nq].clone(), k)
+        cpu_baseline = {
+            "value": nq / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{nq} of the {B} queries x the full {N}-item corpus, fp32 eager torch CPU (oracle/mol_oracle.py), {t:.1f} s",
+        }
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16" if tensor_path else "f32", "data": "synthetic",
+            "config": {
+                "workload": workload_name(args), "parallelism": f"corpus-sharded x{world}" if world > 1 else "single GPU",
+                "mode": args.mode, "tensor_path": bool(tensor_path),
+                "l2_policy": "inputs larger than L2 (bf16 index 640 MB/shard-sum, score matrix 2 GB)",
+            },
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,567 @@
+// C-ABI entry points (include/mol_b200.h): argument checking, workspace carving, kernel sequencing.
+//
+// Path served (reference): rails/indexing/mol_top_k.py:99-130 -> rails/similarities/mol/similarity_fn.py:341-413.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "mol_coarse.cuh"
+
+namespace mol {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional timing of the dominant (scoring) kernel, for bench.py's roofline -----------------
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static size_t g_prof_used = 0;
+static void prof_begin(cudaStream_t st) {
+  if (!g_prof_on) return;
+  if (g_prof_used == g_prof_events.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    g_prof_events.emplace_back(a, b);
+  }
+  cudaEventRecord(g_prof_events[g_prof_used].first, st);
+}
+static void prof_end(cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEventRecord(g_prof_events[g_prof_used].second, st);
+  ++g_prof_used;
+}
+
+static int check_shape(const mol_shape_t* s) {
+  MOL_CHECK_ARG(s != nullptr, "shape is NULL");
+  Dims D = dims_of(*s);
+  MOL_CHECK_ARG(D.Dq > 0 && D.Dx > 0 && D.d > 0 && D.Pq > 0 && D.Px > 0, "non-positive dimension");
+  MOL_CHECK_ARG(D.d % 4 == 0, "dot_product_dimension must be a multiple of 4 (got %d)", D.d);
+  MOL_CHECK_ARG(D.u >= 0 && D.u <= MOL_MAX_UID_TABLES && D.u < D.Pq, "bad num_uid_tables %d", D.u);
+  MOL_CHECK_ARG(D.Hq > 0, "query_hidden_dim must be > 0 (GLU query projection)");
+  MOL_CHECK_ARG(D.Hgq > 0 && D.Hgi > 0, "gating query/item hidden dims must be > 0");
+  MOL_CHECK_ARG(D.H == 128, "gating_qi_hidden_dim must be 128 (got %d)", D.H);
+  MOL_CHECK_ARG(D.L == 32 || D.L == 64 || D.L == 128 || D.L == 256,
+                "P_Q*P_X must be one of 32/64/128/256 (got %d)", D.L);
+  MOL_CHECK_ARG(s->query_nonlinearity == 0 || s->query_nonlinearity == 1, "bad query_nonlinearity");
+  MOL_CHECK_ARG(s->temperature > 0.f, "temperature must be > 0");
+  for (int i = 0; i < D.u; ++i) MOL_CHECK_ARG(s->uid_hash_sizes[i] > 0, "uid hash size must be > 0");
+  return MOL_OK;
+}
+
+static int check_weights(const mol_shape_t* s, const mol_weights_t* w) {
+  MOL_CHECK_ARG(w != nullptr, "weights is NULL");
+  MOL_CHECK_ARG(w->q_glu_w && w->q_glu_b && w->q_out_w && w->q_out_b, "query projection weights missing");
+  MOL_CHECK_ARG(w->x_w && w->x_b, "item projection weights missing");
+  MOL_CHECK_ARG(w->gq_w1 && w->gq_b1 && w->gq_w2, "query-only gating weights missing");
+  MOL_CHECK_ARG(w->gi_w1 && w->gi_b1 && w->gi_w2, "item-only gating weights missing");
+  MOL_CHECK_ARG(w->qi_w1 && w->qi_b1 && w->qi_w2 && w->qi_b2, "qi gating weights missing");
+  for (int i = 0; i < s->num_uid_tables; ++i) MOL_CHECK_ARG(w->uid_emb[i], "uid table %d missing", i);
+  return MOL_OK;
+}
+
+static inline int64_t pad128(int64_t n) { return (n + 127) / 128 * 128; }
+
+// ---- index -----------------------------------------------------------------------------------
+struct IndexLayout {
+  size_t xsub_f32, gi_f32, xsub_bf16, gi_bf16, total;
+};
+static IndexLayout index_layout(const Dims& D, int64_t N) {
+  IndexLayout l;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    off = align_up(off, 1024);
+    size_t r = off;
+    off += bytes;
+    return r;
+  };
+  l.xsub_f32 = take((size_t)N * D.Px * D.d * sizeof(float));
+  l.gi_f32 = take((size_t)N * D.L * sizeof(float));
+  l.xsub_bf16 = take((size_t)pad128(N) * D.Px * D.d * sizeof(uint16_t));
+  l.gi_bf16 = take((size_t)pad128(N) * D.L * sizeof(uint16_t));
+  l.total = align_up(off, 1024);
+  return l;
+}
+
+// ---- search workspace ------------------------------------------------------------------------
+struct SearchWs {
+  // query prologue
+  float *pre, *h, *proj, *hq, *qsub, *gq;
+  float *w1t, *w2t;
+  // host-entry staging
+  float* stage_q;
+  int64_t* stage_uid;
+  float* stage_out_scores;
+  int64_t* stage_out_ids;
+  // scoring / selection
+  float* scores;        // (Bc, N) coarse or exact scores of one query chunk
+  float* seg_scores;    // (Bc, S, kk)
+  int32_t* seg_idx;
+  float* cand_scores;   // (Bc, K') coarse top-K'
+  int32_t* cand_idx;
+  float* exact_scores;  // (Bc, K') rescored
+  int32_t* flags;       // (Bc) fallback flags
+  CoarseWs coarse;
+  int chunk;            // queries per chunk
+  int Kp;               // K' (tensor mode)
+  int S;                // segments for the (chunk, N) select
+  size_t total;
+};
+
+static int coarse_candidates(int k, int64_t N) {
+  // K' = 8k, at least 1024 (rescoring K' pairs costs ~K'/N of the coarse pass, so be generous: the
+  // wider the margin, the rarer the exact fallback), rounded up to 32, capped by N and MOL_MAX_K.
+  int64_t kp = 8 * (int64_t)k;
+  if (kp < 1024) kp = 1024;
+  kp = (kp + 31) / 32 * 32;
+  if (kp > MOL_MAX_K) kp = MOL_MAX_K;
+  if (kp > N) kp = N;
+  if (kp < k) kp = k;
+  return (int)kp;
+}
+
+static bool use_tensor(const mol_shape_t& s, int mode) {
+  if (mode == MOL_MODE_EXACT) return false;
+  return coarse_supported(s);
+}
+
+static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, void* base,
+                       size_t cap, SearchWs* ws) {
+  Dims D = dims_of(s);
+  Arena a(base, cap);
+  const bool tensor = use_tensor(s, mode);
+  ws->pre = a.take<float>((size_t)B * 2 * D.Hq);
+  ws->h = a.take<float>((size_t)B * D.Hq);
+  ws->proj = a.take<float>((size_t)B * D.Pq_proj * D.d);
+  ws->hq = a.take<float>((size_t)B * D.Hgq);
+  ws->qsub = a.take<float>((size_t)B * D.Pq * D.d);
+  ws->gq = a.take<float>((size_t)B * D.L);
+  ws->w1t = a.take<float>((size_t)D.L * D.H);
+  ws->w2t = a.take<float>((size_t)D.L * D.H);
+  ws->stage_q = a.take<float>((size_t)B * D.Dq);
+  ws->stage_uid = a.take<int64_t>((size_t)B);
+  ws->stage_out_scores = a.take<float>((size_t)B * k);
+  ws->stage_out_ids = a.take<int64_t>((size_t)B * k);
+  // query chunk so that the (chunk, N) score matrix stays <= 4 GiB
+  int64_t max_rows = (int64_t)(4ull << 30) / (sizeof(float) * (size_t)(N > 0 ? N : 1));
+  if (max_rows < 1) max_rows = 1;
+  int chunk = (int)(B < max_rows ? B : max_rows);
+  if (chunk < 1) chunk = 1;
+  ws->chunk = chunk;
+  ws->Kp = tensor ? coarse_candidates(k, N) : k;
+  ws->S = select_num_segments(N, chunk, ws->Kp);
+  ws->scores = a.take<float>((size_t)chunk * (size_t)N);
+  ws->seg_scores = a.take<float>((size_t)chunk * ws->S * ws->Kp);
+  ws->seg_idx = a.take<int32_t>((size_t)chunk * ws->S * ws->Kp);
+  ws->cand_scores = a.take<float>((size_t)chunk * ws->Kp);
+  ws->cand_idx = a.take<int32_t>((size_t)chunk * ws->Kp);
+  ws->exact_scores = a.take<float>((size_t)chunk * ws->Kp);
+  ws->flags = a.take<int32_t>((size_t)chunk);
+  memset(&ws->coarse, 0, sizeof(ws->coarse));
+  if (tensor) coarse_plan(s, chunk, a, &ws->coarse);
+  ws->total = align_up(a.off, 256);
+  if (base != nullptr && a.off > cap) {
+    set_error("workspace too small: need %zu bytes, got %zu", ws->total, cap);
+    return MOL_ERR_WORKSPACE;
+  }
+  return MOL_OK;
+}
+
+static int run_query_prologue(const mol_shape_t& s, const mol_weights_t& w, const float* queries,
+                              const int64_t* user_ids, int B, float* pre, float* h, float* proj,
+                              float* hq, float* qsub, float* gq, cudaStream_t st) {
+  Dims D = dims_of(s);
+  // query_embeddings_fns.py:191-197 : Linear(GLU(q))
+  MOL_TRY(launch_linear(queries, w.q_glu_w, w.q_glu_b, pre, B, 2 * D.Hq, D.Dq, /*w_sn=*/1,
+                        /*w_sk=*/2 * D.Hq, ACT_NONE, st));
+  MOL_TRY(launch_glu(pre, h, B, D.Hq, s.query_nonlinearity, st));
+  MOL_TRY(launch_linear(h, w.q_out_w, w.q_out_b, proj, B, D.Pq_proj * D.d, D.Hq, D.Hq, 1, ACT_NONE, st));
+  MOL_TRY(launch_query_assemble(s, w, proj, user_ids, qsub, B, st));
+  // similarity_fn.py:166-169 : query-only gating partial
+  MOL_TRY(launch_linear(queries, w.gq_w1, w.gq_b1, hq, B, D.Hgq, D.Dq, D.Dq, 1, ACT_SILU, st));
+  MOL_TRY(launch_linear(hq, w.gq_w2, nullptr, gq, B, D.L, D.Hgq, D.Hgq, 1, ACT_NONE, st));
+  return MOL_OK;
+}
+
+static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_index_t& ix,
+                       const float* queries, const int64_t* user_ids, int B, int k, int mode,
+                       float* out_scores, int64_t* out_ids, const SearchWs& ws, cudaStream_t st) {
+  Dims D = dims_of(s);
+  const int64_t N = ix.num_items;
+  const bool tensor = use_tensor(s, mode);
+  MOL_TRY(run_query_prologue(s, w, queries, user_ids, B, ws.pre, ws.h, ws.proj, ws.hq, ws.qsub,
+                             ws.gq, st));
+  MOL_TRY(launch_transpose(w.qi_w1, ws.w1t, D.H, D.L, st));  // (H,L) -> (L,H)
+  MOL_TRY(launch_transpose(w.qi_w2, ws.w2t, D.L, D.H, st));  // (L,H) -> (H,L)
+  if (tensor) MOL_TRY(coarse_prepare(s, w, ws.coarse, st));
+
+  for (int b0 = 0; b0 < B; b0 += ws.chunk) {
+    const int bc = (B - b0 < ws.chunk) ? (B - b0) : ws.chunk;
+    const float* qsub = ws.qsub + (size_t)b0 * D.Pq * D.d;
+    const float* gq = ws.gq + (size_t)b0 * D.L;
+    float* o_scores = out_scores + (size_t)b0 * k;
+    int64_t* o_ids = out_ids + (size_t)b0 * k;
+    const int kk = tensor ? ws.Kp : k;
+    prof_begin(st);
+    if (tensor) {
+      MOL_TRY(coarse_scores(s, ix, ws.coarse, qsub, gq, bc, ws.scores, st));
+    } else {
+      MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub, gq, bc, nullptr, N, N, ws.scores,
+                                  nullptr, st));
+    }
+    prof_end(st);
+    // top-kk of each row of the (bc, N) score matrix
+    const float* sel_scores = ws.scores;
+    const int32_t* sel_payload = nullptr;
+    int64_t sel_n = N, sel_ld = N;
+    if (ws.S > 1) {
+      MOL_TRY(launch_select_segments(ws.scores, N, N, bc, ws.S, kk, ws.seg_scores, ws.seg_idx,
+                                     nullptr, st));
+      sel_scores = ws.seg_scores;
+      sel_payload = ws.seg_idx;
+      sel_n = (int64_t)ws.S * kk;
+      sel_ld = sel_n;
+    }
+    if (!tensor) {
+      MOL_TRY(launch_select_final_i32(sel_scores, sel_payload, sel_n, sel_ld, bc, k, o_scores,
+                                      nullptr, o_ids, ix.item_ids, nullptr, st));
+    } else {
+      // coarse top-K' -> exact fp32 rescoring -> final top-k (+ safety check and per-query fallback)
+      MOL_TRY(launch_select_final_i32(sel_scores, sel_payload, sel_n, sel_ld, bc, kk,
+                                      ws.cand_scores, ws.cand_idx, nullptr, nullptr, nullptr, st));
+      MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub, gq, bc, ws.cand_idx, kk, kk,
+                                  ws.exact_scores, nullptr, st));
+      MOL_TRY(launch_select_final_i32(ws.exact_scores, ws.cand_idx, kk, kk, bc, k, o_scores,
+                                      nullptr, o_ids, ix.item_ids, nullptr, st));
+      if (kk < N) {
+        MOL_TRY(coarse_safety_flags(ws.cand_scores, ws.exact_scores, o_scores, bc, kk, k, ws.flags, st));
+        // flagged queries are re-done exactly (kernels exit immediately for unflagged rows)
+        MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub, gq, bc, nullptr, N, N,
+                                    ws.scores, ws.flags, st));
+        const float* f_scores = ws.scores;
+        const int32_t* f_payload = nullptr;
+        int64_t f_n = N, f_ld = N;
+        if (ws.S > 1) {
+          MOL_TRY(launch_select_segments(ws.scores, N, N, bc, ws.S, kk, ws.seg_scores, ws.seg_idx,
+                                         ws.flags, st));
+          f_scores = ws.seg_scores;
+          f_payload = ws.seg_idx;
+          f_n = (int64_t)ws.S * kk;
+          f_ld = f_n;
+        }
+        MOL_TRY(launch_select_final_i32(f_scores, f_payload, f_n, f_ld, bc, k, o_scores, nullptr,
+                                        o_ids, ix.item_ids, ws.flags, st));
+      }
+    }
+  }
+  return MOL_OK;
+}
+
+}  // namespace mol
+
+using namespace mol;
+
+extern "C" {
+
+const char* mol_version(void) { return "rails_b200 0.1 (sm_100a)"; }
+const char* mol_last_error(void) { return g_err; }
+int64_t mol_launch_count(void) { return g_launches.load(); }
+void mol_launch_count_reset(void) { g_launches.store(0); }
+
+void mol_profile_enable(int32_t on) {
+  g_prof_on = on != 0;
+  g_prof_used = 0;
+}
+
+int mol_profile_collect(double* total_ms, int32_t* launches) {
+  MOL_CHECK_ARG(total_ms && launches, "NULL output");
+  double t = 0.0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    MOL_CUDA(cudaEventSynchronize(g_prof_events[i].second));
+    float ms = 0.f;
+    MOL_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i].first, g_prof_events[i].second));
+    t += ms;
+  }
+  *total_ms = t;
+  *launches = (int32_t)g_prof_used;
+  g_prof_used = 0;
+  return MOL_OK;
+}
+
+int mol_shape_check(const mol_shape_t* shape, int32_t* tensor_ok) {
+  MOL_TRY(check_shape(shape));
+  if (tensor_ok) *tensor_ok = coarse_supported(*shape) ? 1 : 0;
+  return MOL_OK;
+}
+
+int mol_index_bytes(const mol_shape_t* shape, int64_t num_items, size_t* bytes) {
+  MOL_TRY(check_shape(shape));
+  MOL_CHECK_ARG(num_items >= 0 && bytes, "bad arguments");
+  MOL_CHECK_ARG(num_items < (1ll << 31) - 256, "num_items per shard must fit int32");
+  *bytes = index_layout(dims_of(*shape), num_items).total;
+  return MOL_OK;
+}
+
+int mol_index_layout(const mol_shape_t* shape, int64_t num_items, const float* raw_items,
+                     const int64_t* item_ids, void* blob, size_t blob_bytes, mol_index_t* index) {
+  MOL_TRY(check_shape(shape));
+  MOL_CHECK_ARG(index && blob, "index/blob is NULL");
+  MOL_CHECK_ARG(num_items >= 0 && num_items < (1ll << 31) - 256, "bad num_items");
+  IndexLayout l = index_layout(dims_of(*shape), num_items);
+  MOL_CHECK_ARG(blob_bytes >= l.total, "index blob too small: need %zu, got %zu", l.total, blob_bytes);
+  MOL_CHECK_ARG((reinterpret_cast<uintptr_t>(blob) & 1023) == 0, "index blob must be 1024-byte aligned");
+  char* p = static_cast<char*>(blob);
+  index->num_items = num_items;
+  index->raw_items = raw_items;
+  index->item_ids = item_ids;
+  index->xsub_f32 = reinterpret_cast<float*>(p + l.xsub_f32);
+  index->gi_f32 = reinterpret_cast<float*>(p + l.gi_f32);
+  index->xsub_bf16 = reinterpret_cast<uint16_t*>(p + l.xsub_bf16);
+  index->gi_bf16 = reinterpret_cast<uint16_t*>(p + l.gi_bf16);
+  return MOL_OK;
+}
+
+int mol_index_build_workspace_bytes(const mol_shape_t* shape, int64_t num_items, size_t* bytes) {
+  MOL_TRY(check_shape(shape));
+  MOL_CHECK_ARG(bytes, "bytes is NULL");
+  Dims D = dims_of(*shape);
+  int cols = D.Px * D.d > D.Hgi ? D.Px * D.d : D.Hgi;
+  *bytes = align_up((size_t)num_items * cols * sizeof(float), 256) + 256;
+  return MOL_OK;
+}
+
+int mol_index_build(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
+                    void* workspace, size_t workspace_bytes, mol_stream_t stream) {
+  MOL_TRY(check_shape(shape));
+  MOL_TRY(check_weights(shape, w));
+  MOL_CHECK_ARG(index && index->raw_items, "index / raw_items is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Dims D = dims_of(*shape);
+  const int64_t N = index->num_items;
+  size_t need;
+  MOL_TRY(mol_index_build_workspace_bytes(shape, N, &need));
+  if (workspace_bytes < need || (N > 0 && !workspace)) {
+    set_error("index build workspace too small: need %zu, got %zu", need, workspace_bytes);
+    return MOL_ERR_WORKSPACE;
+  }
+  float* tmp = static_cast<float*>(workspace);
+  const int64_t Np = pad128(N);
+  // zero the bf16 pad rows (and everything else) so the tensor-core pass can read whole tiles
+  MOL_CUDA(cudaMemsetAsync(index->xsub_bf16, 0, (size_t)Np * D.Px * D.d * sizeof(uint16_t), st));
+  MOL_CUDA(cudaMemsetAsync(index->gi_bf16, 0, (size_t)Np * D.L * sizeof(uint16_t), st));
+  // item_embeddings_fns.py:165-182
+  MOL_TRY(launch_linear(index->raw_items, w->x_w, w->x_b, tmp, N, D.Px * D.d, D.Dx, D.Dx, 1, ACT_NONE, st));
+  MOL_TRY(launch_l2norm_groups(tmp, index->xsub_f32, reinterpret_cast<__nv_bfloat16*>(index->xsub_bf16),
+                               N, D.Px, D.d, shape->eps, st));
+  // similarity_fn.py:170-171
+  MOL_TRY(launch_linear(index->raw_items, w->gi_w1, w->gi_b1, tmp, N, D.Hgi, D.Dx, D.Dx, 1, ACT_SILU, st));
+  MOL_TRY(launch_linear(tmp, w->gi_w2, nullptr, index->gi_f32, N, D.L, D.Hgi, D.Hgi, 1, ACT_NONE, st));
+  MOL_TRY(launch_f32_to_bf16(index->gi_f32, reinterpret_cast<__nv_bfloat16*>(index->gi_bf16),
+                             N * D.L, st));
+  return MOL_OK;
+}
+
+int mol_search_workspace_bytes(const mol_shape_t* shape, int64_t num_items, int32_t B, int32_t k,
+                               int32_t mode, size_t* bytes) {
+  MOL_TRY(check_shape(shape));
+  MOL_CHECK_ARG(bytes && B >= 0 && k >= 0 && num_items >= 0, "bad arguments");
+  MOL_CHECK_ARG(mode != MOL_MODE_TENSOR || coarse_supported(*shape), "shape not supported by the tensor-core path");
+  SearchWs ws;
+  MOL_TRY(plan_search(*shape, num_items, B > 0 ? B : 1, k > 0 ? k : 1, mode, nullptr, 0, &ws));
+  *bytes = ws.total + 256;
+  return MOL_OK;
+}
+
+static int check_search_args(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
+                             const void* queries, const void* user_ids, int32_t B, int32_t k,
+                             int32_t mode, const void* out_scores, const void* out_ids) {
+  MOL_TRY(check_shape(shape));
+  MOL_TRY(check_weights(shape, w));
+  MOL_CHECK_ARG(index && index->xsub_f32 && index->gi_f32, "index not laid out");
+  MOL_CHECK_ARG(B >= 0, "negative batch");
+  MOL_CHECK_ARG(k >= 1, "k must be >= 1 (got %d)", k);
+  if (k > index->num_items) {
+    set_error("selected index k out of range (k=%d > %lld items)", k, (long long)index->num_items);
+    return MOL_ERR_RANGE;
+  }
+  MOL_CHECK_ARG(k <= MOL_MAX_K, "k=%d exceeds MOL_MAX_K=%d", k, MOL_MAX_K);
+  MOL_CHECK_ARG(B == 0 || (queries && out_scores && out_ids), "NULL query/output buffer");
+  MOL_CHECK_ARG(shape->num_uid_tables == 0 || B == 0 || user_ids, "user_ids required when uid embeddings are configured");
+  MOL_CHECK_ARG(mode == MOL_MODE_AUTO || mode == MOL_MODE_EXACT || mode == MOL_MODE_TENSOR, "bad mode %d", mode);
+  MOL_CHECK_ARG(mode != MOL_MODE_TENSOR || coarse_supported(*shape), "shape not supported by the tensor-core path");
+  return MOL_OK;
+}
+
+int mol_search(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
+               const float* queries, const int64_t* user_ids, int32_t B, int32_t k, int32_t sorted,
+               int32_t mode, float* out_scores, int64_t* out_ids, void* workspace,
+               size_t workspace_bytes, mol_stream_t stream) {
+  (void)sorted;  // results are always sorted; a sorted list is a valid unsorted answer
+  MOL_TRY(check_search_args(shape, w, index, queries, user_ids, B, k, mode, out_scores, out_ids));
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(workspace, "workspace is NULL");
+  SearchWs ws;
+  MOL_TRY(plan_search(*shape, index->num_items, B, k, mode, workspace, workspace_bytes, &ws));
+  return search_impl(*shape, *w, *index, queries, user_ids, B, k, mode, out_scores, out_ids, ws,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int mol_search_host(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
+                    const float* host_queries, const int64_t* host_user_ids, int32_t B, int32_t k,
+                    int32_t sorted, int32_t mode, float* host_out_scores, int64_t* host_out_ids,
+                    void* workspace, size_t workspace_bytes, mol_stream_t stream) {
+  (void)sorted;
+  MOL_TRY(check_search_args(shape, w, index, host_queries, host_user_ids, B, k, mode, host_out_scores,
+                            host_out_ids));
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(workspace, "workspace is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SearchWs ws;
+  MOL_TRY(plan_search(*shape, index->num_items, B, k, mode, workspace, workspace_bytes, &ws));
+  Dims D = dims_of(*shape);
+  MOL_CUDA(cudaMemcpyAsync(ws.stage_q, host_queries, (size_t)B * D.Dq * sizeof(float),
+                           cudaMemcpyHostToDevice, st));
+  const int64_t* uid = nullptr;
+  if (D.u > 0) {
+    MOL_CUDA(cudaMemcpyAsync(ws.stage_uid, host_user_ids, (size_t)B * sizeof(int64_t),
+                             cudaMemcpyHostToDevice, st));
+    uid = ws.stage_uid;
+  }
+  MOL_TRY(search_impl(*shape, *w, *index, ws.stage_q, uid, B, k, mode, ws.stage_out_scores,
+                      ws.stage_out_ids, ws, st));
+  MOL_CUDA(cudaMemcpyAsync(host_out_scores, ws.stage_out_scores, (size_t)B * k * sizeof(float),
+                           cudaMemcpyDeviceToHost, st));
+  MOL_CUDA(cudaMemcpyAsync(host_out_ids, ws.stage_out_ids, (size_t)B * k * sizeof(int64_t),
+                           cudaMemcpyDeviceToHost, st));
+  MOL_CUDA(cudaStreamSynchronize(st));
+  return MOL_OK;
+}
+
+int mol_score_all(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
+                  const float* queries, const int64_t* user_ids, int32_t B, float* out_scores,
+                  void* workspace, size_t workspace_bytes, mol_stream_t stream) {
+  MOL_TRY(check_shape(shape));
+  MOL_TRY(check_weights(shape, w));
+  MOL_CHECK_ARG(index && index->xsub_f32 && index->gi_f32, "index not laid out");
+  MOL_CHECK_ARG(B >= 0, "negative batch");
+  if (B == 0 || index->num_items == 0) return MOL_OK;
+  MOL_CHECK_ARG(queries && out_scores && workspace, "NULL buffer");
+  MOL_CHECK_ARG(shape->num_uid_tables == 0 || user_ids, "user_ids required when uid embeddings are configured");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SearchWs ws;
+  MOL_TRY(plan_search(*shape, /*N=*/1, B, 1, MOL_MODE_EXACT, workspace, workspace_bytes, &ws));
+  Dims D = dims_of(*shape);
+  MOL_TRY(run_query_prologue(*shape, *w, queries, user_ids, B, ws.pre, ws.h, ws.proj, ws.hq, ws.qsub,
+                             ws.gq, st));
+  MOL_TRY(launch_transpose(w->qi_w1, ws.w1t, D.H, D.L, st));
+  MOL_TRY(launch_transpose(w->qi_w2, ws.w2t, D.L, D.H, st));
+  return launch_exact_scores(*shape, *w, *index, ws.w1t, ws.w2t, ws.qsub, ws.gq, B, nullptr,
+                             index->num_items, index->num_items, out_scores, nullptr, st);
+}
+
+int mol_query_prologue(const mol_shape_t* shape, const mol_weights_t* w, const float* queries,
+                       const int64_t* user_ids, int32_t B, float* out_qsub, float* out_gq,
+                       void* workspace, size_t workspace_bytes, mol_stream_t stream) {
+  MOL_TRY(check_shape(shape));
+  MOL_TRY(check_weights(shape, w));
+  MOL_CHECK_ARG(B >= 0, "negative batch");
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(queries && out_qsub && out_gq && workspace, "NULL buffer");
+  MOL_CHECK_ARG(shape->num_uid_tables == 0 || user_ids, "user_ids required when uid embeddings are configured");
+  SearchWs ws;
+  MOL_TRY(plan_search(*shape, 1, B, 1, MOL_MODE_EXACT, workspace, workspace_bytes, &ws));
+  return run_query_prologue(*shape, *w, queries, user_ids, B, ws.pre, ws.h, ws.proj, ws.hq, out_qsub,
+                            out_gq, static_cast<cudaStream_t>(stream));
+}
+
+int mol_topk_workspace_bytes(int64_t n, int32_t B, int32_t k, size_t* bytes) {
+  MOL_CHECK_ARG(bytes && n >= 0 && B >= 0 && k >= 1, "bad arguments");
+  int S = select_num_segments(n, B > 0 ? B : 1, k);
+  *bytes = 2 * align_up((size_t)(B > 0 ? B : 1) * S * k * sizeof(float), 256) + 512;
+  return MOL_OK;
+}
+
+int mol_topk(const float* scores, int64_t n, int64_t ld, int32_t B, int32_t k, const int64_t* id_map,
+             float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+             mol_stream_t stream) {
+  MOL_CHECK_ARG(B >= 0 && k >= 1 && k <= MOL_MAX_K && n >= 0 && ld >= n, "bad arguments");
+  MOL_CHECK_ARG(n < (1ll << 31) - 256, "n must fit int32");
+  if (k > n) {
+    set_error("selected index k out of range (k=%d > %lld columns)", k, (long long)n);
+    return MOL_ERR_RANGE;
+  }
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(scores && out_scores && out_idx, "NULL buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int S = select_num_segments(n, B, k);
+  if (S == 1)
+    return launch_select_final_i32(scores, nullptr, n, ld, B, k, out_scores, nullptr, out_idx, id_map, nullptr, st);
+  size_t need;
+  MOL_TRY(mol_topk_workspace_bytes(n, B, k, &need));
+  if (!workspace || workspace_bytes < need) {
+    set_error("topk workspace too small: need %zu, got %zu", need, workspace_bytes);
+    return MOL_ERR_WORKSPACE;
+  }
+  Arena a(workspace, workspace_bytes);
+  float* ss = a.take<float>((size_t)B * S * k);
+  int32_t* si = a.take<int32_t>((size_t)B * S * k);
+  MOL_TRY(launch_select_segments(scores, n, ld, B, S, k, ss, si, nullptr, st));
+  return launch_select_final_i32(ss, si, (int64_t)S * k, (int64_t)S * k, B, k, out_scores, nullptr, out_idx,
+                                 id_map, nullptr, st);
+}
+
+int mol_merge_topk_workspace_bytes(int32_t R, int32_t B, int32_t k, size_t* bytes) {
+  MOL_CHECK_ARG(bytes && R >= 1 && B >= 0 && k >= 1, "bad arguments");
+  *bytes = align_up((size_t)R * B * k * sizeof(float), 256) + (size_t)R * B * k * sizeof(int64_t) + 512;
+  return MOL_OK;
+}
+
+// parts are (R, B, k); the select kernel wants (B, R*k) rows -> handled by a strided view: we launch
+// one merge per query row with ld = k and gather the R parts through a small transpose kernel.
+__global__ void merge_gather_kernel(const float* __restrict__ ps, const int64_t* __restrict__ pi,
+                                    float* __restrict__ os, int64_t* __restrict__ oi, int R, int B, int k) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)R * B * k;
+  if (i >= total) return;
+  int r = (int)(i / ((int64_t)B * k));
+  int64_t rem = i % ((int64_t)B * k);
+  int b = (int)(rem / k), j = (int)(rem % k);
+  int64_t o = ((int64_t)b * R + r) * k + j;
+  os[o] = ps[i];
+  oi[o] = pi[i];
+}
+
+int mol_merge_topk(const float* part_scores, const int64_t* part_ids, int32_t R, int32_t B,
+                   int32_t k, float* out_scores, int64_t* out_ids, void* workspace,
+                   size_t workspace_bytes, mol_stream_t stream) {
+  MOL_CHECK_ARG(R >= 1 && B >= 0 && k >= 1 && k <= MOL_MAX_K, "bad arguments");
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(part_scores && part_ids && out_scores && out_ids, "NULL buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t need = align_up((size_t)R * B * k * sizeof(float), 256) + (size_t)R * B * k * sizeof(int64_t) + 256;
+  if (!workspace || workspace_bytes < need) {
+    set_error("merge workspace too small: need %zu, got %zu", need, workspace_bytes);
+    return MOL_ERR_WORKSPACE;
+  }
+  Arena a(workspace, workspace_bytes);
+  float* gs = a.take<float>((size_t)R * B * k);
+  int64_t* gi = a.take<int64_t>((size_t)R * B * k);
+  int64_t total = (int64_t)R * B * k;
+  merge_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part_scores, part_ids, gs, gi, R, B, k);
+  MOL_LAUNCH_CHECK();
+  return launch_select_final_i64(gs, gi, (int64_t)R * k, (int64_t)R * k, B, k, out_scores, out_ids, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+// Item-side index build and query prologue kernels (fp32 CUDA cores).
+//
+// Reference arithmetic followed (see oracle/mol_oracle.py for the CPU restatement):
+//   rails/similarities/mol/item_embeddings_fns.py:165-182   Linear -> reshape (P_X, d) -> l2 norm
+//   rails/similarities/mol/query_embeddings_fns.py:191-253  GLU-MLP -> reshape -> cat uid emb -> l2 norm
+//   rails/similarities/layers.py:36-43, 67-74               GeGLU / SwiGLU
+//   rails/similarities/mol/similarity_fn.py:166-171         query-only / item-only gating MLPs
+// These run once per corpus (index build) or are O(B) (query prologue); SURVEY.md §8 (f1) lists
+// their fused/tensor-core versions as "next".
+#include "common.cuh"
+
+namespace mol {
+
+// ------------------------------------------------------------------------------------------
+// Tiled fp32 GEMM:  C[M,N] = act(A[M,K] W^T + bias),  64x64 tile, 16-deep K slab, 4x4 per thread.
+// ------------------------------------------------------------------------------------------
+constexpr int LT_M = 64, LT_N = 64, LT_K = 16;
+
+template <int ACT>
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A,
+                                                     const float* __restrict__ W,
+                                                     const float* __restrict__ bias,
+                                                     float* __restrict__ C, int64_t M, int N, int K,
+                                                     int64_t w_sn, int64_t w_sk) {
+  __shared__ float As[LT_K][LT_M + 4];
+  __shared__ float Ws[LT_K][LT_N + 4];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * LT_M;
+  const int n0 = blockIdx.y * LT_N;
+  const int tx = tid % 16, ty = tid / 16;  // tx -> n, ty -> m
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += LT_K) {
+    // A tile: 64 rows x 16 k; consecutive threads walk k (contiguous in memory).
+    for (int e = tid; e < LT_M * LT_K; e += 256) {
+      int r = e / LT_K, kk = e % LT_K;
+      int64_t m = m0 + r;
+      int k = k0 + kk;
+      As[kk][r] = (m < M && k < K) ? A[m * K + k] : 0.f;
+    }
+    for (int e = tid; e < LT_N * LT_K; e += 256) {
+      int r, kk;
+      if (w_sk == 1) {  // (n,k) with k contiguous
+        r = e / LT_K;
+        kk = e % LT_K;
+      } else {  // (k,n) with n contiguous
+        kk = e / LT_N;
+        r = e % LT_N;
+      }
+      int n = n0 + r, k = k0 + kk;
+      Ws[kk][r] = (n < N && k < K) ? W[n * w_sn + k * w_sk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < LT_K; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (ACT == ACT_SILU) v = v / (1.f + expf(-v));
+      C[m * N + n] = v;
+    }
+  }
+}
+
+int launch_linear(const float* A, const float* W, const float* bias, float* C, int64_t M, int N,
+                  int K, int64_t w_sn, int64_t w_sk, Act act, cudaStream_t st) {
+  if (M == 0 || N == 0) return MOL_OK;
+  dim3 grid((unsigned)((M + LT_M - 1) / LT_M), (unsigned)((N + LT_N - 1) / LT_N));
+  if (act == ACT_SILU)
+    linear_kernel<ACT_SILU><<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K, w_sn, w_sk);
+  else
+    linear_kernel<ACT_NONE><<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K, w_sn, w_sk);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void glu_kernel(const float* __restrict__ pre, float* __restrict__ h, int64_t total,
+                           int Hq, int kind) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t b = i / Hq;
+  int j = (int)(i % Hq);
+  float lhs = pre[b * 2 * Hq + j], rhs = pre[b * 2 * Hq + Hq + j];
+  float a;
+  if (kind == 0) {
+    a = 0.5f * lhs * (1.f + erff(lhs * 0.70710678118654752440f));  // F.gelu (erf form)
+  } else {
+    a = lhs / (1.f + expf(-lhs));  // F.silu
+  }
+  h[i] = a * rhs;
+}
+
+int launch_glu(const float* pre, float* h, int64_t B, int Hq, int kind, cudaStream_t st) {
+  int64_t total = B * Hq;
+  if (total == 0) return MOL_OK;
+  glu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pre, h, total, Hq, kind);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// One warp per d-vector.
+__global__ void l2norm_groups_kernel(const float* __restrict__ in, float* __restrict__ out_f32,
+                                     __nv_bfloat16* __restrict__ out_bf16, int64_t n_vec, int d,
+                                     float eps) {
+  int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  int lane = threadIdx.x % 32;
+  if (v >= n_vec) return;
+  const float* p = in + v * d;
+  float ss = 0.f;
+  for (int i = lane; i < d; i += 32) ss = fmaf(p[i], p[i], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  float nrm = fmaxf(sqrtf(ss), eps);
+  for (int i = lane; i < d; i += 32) {
+    float y = p[i] / nrm;
+    if (out_f32) out_f32[v * d + i] = y;
+    if (out_bf16) out_bf16[v * d + i] = __float2bfloat16_rn(y);
+  }
+}
+
+int launch_l2norm_groups(const float* in, float* out_f32, __nv_bfloat16* out_bf16, int64_t rows,
+                         int groups, int d, float eps, cudaStream_t st) {
+  int64_t n_vec = rows * groups;
+  if (n_vec == 0) return MOL_OK;
+  int64_t threads = n_vec * 32;
+  l2norm_groups_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, out_f32, out_bf16,
+                                                                          n_vec, d, eps);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+struct UidTables {
+  const float* emb[MOL_MAX_UID_TABLES];
+  int hash[MOL_MAX_UID_TABLES];
+};
+
+// One warp per (b, n): n < Pq_proj reads the projected vector, else the uid-embedding row
+// (user_ids % hash) + 1  (query_embeddings_fns.py:205-207), then l2-normalises.
+__global__ void query_assemble_kernel(const float* __restrict__ proj,
+                                      const int64_t* __restrict__ user_ids, UidTables t,
+                                      float* __restrict__ qsub, int B, int Pq, int Pq_proj, int d,
+                                      float eps) {
+  int v = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  int lane = threadIdx.x % 32;
+  if (v >= B * Pq) return;
+  int b = v / Pq, n = v % Pq;
+  const float* p;
+  if (n < Pq_proj) {
+    p = proj + ((int64_t)b * Pq_proj + n) * d;
+  } else {
+    int ti = n - Pq_proj;
+    int64_t h = t.hash[ti];
+    int64_t r = user_ids[b] % h;
+    if (r < 0) r += h;  // python-style modulo
+    p = t.emb[ti] + (r + 1) * d;
+  }
+  float ss = 0.f;
+  for (int i = lane; i < d; i += 32) ss = fmaf(p[i], p[i], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  float nrm = fmaxf(sqrtf(ss), eps);
+  for (int i = lane; i < d; i += 32) qsub[(int64_t)v * d + i] = p[i] / nrm;
+}
+
+int launch_query_assemble(const mol_shape_t& s, const mol_weights_t& w, const float* proj,
+                          const int64_t* user_ids, float* qsub, int B, cudaStream_t st) {
+  Dims D = dims_of(s);
+  if (B == 0) return MOL_OK;
+  UidTables t;
+  for (int i = 0; i < MOL_MAX_UID_TABLES; ++i) {
+    t.emb[i] = i < D.u ? w.uid_emb[i] : nullptr;
+    t.hash[i] = i < D.u ? s.uid_hash_sizes[i] : 1;
+  }
+  int threads = B * D.Pq * 32;
+  query_assemble_kernel<<<(threads + 255) / 256, 256, 0, st>>>(proj, user_ids, t, qsub, B, D.Pq,
+                                                               D.Pq_proj, D.d, s.eps);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                   int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t st) {
+  if (n == 0) return MOL_OK;
+  f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
+}  // namespace mol

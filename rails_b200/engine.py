@@ -1,0 +1,326 @@
+"""Host-side glue between the torch modules and the C ABI (include/mol_b200.h).
+
+PyTorch is used for device memory (caller-owned buffers handed to the library as raw pointers) and
+for the current CUDA stream — nothing else.  Every arithmetic step of the path runs in
+libmol_b200.so; there is no torch / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from rails_b200 import _lib
+from rails_b200._lib import MolIndex, MolShape, MolWeights, byref, c_int32, c_size_t
+
+# state-dict keys of the reference MoLSimilarity (modeling/similarity_utils.py:72-214)
+K_Q_GLU_W = "_query_embeddings_fn._query_emb_proj_module.1._w"
+K_Q_GLU_B = "_query_embeddings_fn._query_emb_proj_module.1._b"
+K_Q_OUT_W = "_query_embeddings_fn._query_emb_proj_module.2.weight"
+K_Q_OUT_B = "_query_embeddings_fn._query_emb_proj_module.2.bias"
+K_UID = "_query_embeddings_fn._uid_embeddings_{}.weight"
+K_X_W = "_item_embeddings_fn._item_emb_proj_module.1.weight"
+K_X_B = "_item_embeddings_fn._item_emb_proj_module.1.bias"
+K_GQ_W1 = "_gating_fn._query_only_partial_module.0.weight"
+K_GQ_B1 = "_gating_fn._query_only_partial_module.0.bias"
+K_GQ_W2 = "_gating_fn._query_only_partial_module.2.weight"
+K_GI_W1 = "_gating_fn._item_only_partial_module.1.weight"
+K_GI_B1 = "_gating_fn._item_only_partial_module.1.bias"
+K_GI_W2 = "_gating_fn._item_only_partial_module.3.weight"
+K_QI_W1 = "_gating_fn._qi_partial_module.1.weight"
+K_QI_B1 = "_gating_fn._qi_partial_module.1.bias"
+K_QI_W2 = "_gating_fn._qi_partial_module.3.weight"
+K_QI_B2 = "_gating_fn._qi_partial_module.3.bias"
+
+_FIELD_OF_KEY = {
+    K_Q_GLU_W: "q_glu_w", K_Q_GLU_B: "q_glu_b", K_Q_OUT_W: "q_out_w", K_Q_OUT_B: "q_out_b",
+    K_X_W: "x_w", K_X_B: "x_b",
+    K_GQ_W1: "gq_w1", K_GQ_B1: "gq_b1", K_GQ_W2: "gq_w2",
+    K_GI_W1: "gi_w1", K_GI_B1: "gi_b1", K_GI_W2: "gi_w2",
+    K_QI_W1: "qi_w1", K_QI_B1: "qi_b1", K_QI_W2: "qi_w2", K_QI_B2: "qi_b2",
+}
+
+
+def _stream_ptr(device: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} must live on a CUDA device: rails_b200 runs the MoL top-k path only through its "
+            "sm_100a CUDA library (no CPU fallback)"
+        )
+
+
+class PackedWeights:
+    """fp32, contiguous, device-resident views/copies of the module's parameters + the C structs."""
+
+    def __init__(self, state: Dict[str, torch.Tensor], shape: MolShape, device: torch.device) -> None:
+        self.device = device
+        self.shape = shape
+        self.keep: List[torch.Tensor] = []
+        self.struct = MolWeights()
+        for key, field in _FIELD_OF_KEY.items():
+            if key not in state:
+                raise ValueError(f"MoL weights: missing parameter {key}")
+            setattr(self.struct, field, self._dev(state[key]).data_ptr())
+        for i in range(shape.num_uid_tables):
+            key = K_UID.format(i)
+            if key not in state:
+                raise ValueError(f"MoL weights: missing parameter {key}")
+            self.struct.uid_emb[i] = self._dev(state[key]).data_ptr()
+
+    def _dev(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self.keep.append(t)
+        return t
+
+
+class Workspace:
+    """Grow-only device scratch, owned by the caller side of the ABI."""
+
+    def __init__(self, device: torch.device) -> None:
+        self.device = device
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+class IndexHandle:
+    """The item-side cache of one corpus (shard): blob + C struct + borrowed caller tensors."""
+
+    def __init__(self, weights: PackedWeights, raw_items: torch.Tensor, item_ids: Optional[torch.Tensor]) -> None:
+        lib = _lib.load()
+        _require_cuda(raw_items, "item_embeddings")
+        if raw_items.dim() != 2:
+            raise ValueError(f"raw items must be (N, D), got {tuple(raw_items.shape)}")
+        if raw_items.size(1) != weights.shape.item_embedding_dim:
+            raise ValueError(
+                f"item_embeddings last dim {raw_items.size(1)} != item_embedding_dim {weights.shape.item_embedding_dim}"
+            )
+        self.weights = weights
+        self.device = raw_items.device
+        self.raw = raw_items.detach().to(torch.float32).contiguous()
+        self.ids = None if item_ids is None else item_ids.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        self.N = int(self.raw.size(0))
+        if self.ids is not None and self.ids.numel() != self.N:
+            raise ValueError(f"item_ids has {self.ids.numel()} entries for {self.N} items")
+        nbytes = c_size_t()
+        _lib.check(lib.mol_index_bytes(byref(weights.shape), self.N, byref(nbytes)))
+        self.blob = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=self.device)
+        base = (self.blob.data_ptr() + 1023) // 1024 * 1024
+        self.struct = MolIndex()
+        _lib.check(
+            lib.mol_index_layout(
+                byref(weights.shape), self.N, _ptr(self.raw), _ptr(self.ids), ctypes.c_void_p(base),
+                nbytes.value, byref(self.struct),
+            )
+        )
+        ws_bytes = c_size_t()
+        _lib.check(lib.mol_index_build_workspace_bytes(byref(weights.shape), self.N, byref(ws_bytes)))
+        ws = torch.empty(max(ws_bytes.value, 1), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(
+                lib.mol_index_build(
+                    byref(weights.shape), byref(weights.struct), byref(self.struct), _ptr(ws), ws_bytes.value,
+                    _stream_ptr(self.device),
+                )
+            )
+        # `ws` may be freed after this point: the caching allocator is stream-ordered on the current stream.
+
+    def xsub_f32(self) -> torch.Tensor:
+        """(N, P_X, d) fp32 view of the cached item sub-embeddings (a copy, detached from the blob)."""
+        s = self.weights.shape
+        n = self.N * s.item_dot_product_groups * s.dot_product_dimension
+        off = self.struct.xsub_f32 - self.blob.data_ptr()
+        return (
+            self.blob[off : off + 4 * n].view(torch.float32)
+            .view(self.N, s.item_dot_product_groups, s.dot_product_dimension).clone()
+        )
+
+
+def search(
+    weights: PackedWeights,
+    index: IndexHandle,
+    workspace: Workspace,
+    queries: torch.Tensor,
+    user_ids: Optional[torch.Tensor],
+    k: int,
+    sorted: bool = True,
+    mode: int = _lib.MODE_AUTO,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """mol_search with device buffers.  Returns (scores (B,k) fp32, ids (B,k) int64)."""
+    lib = _lib.load()
+    _require_cuda(queries, "query_embeddings")
+    dev = index.device
+    q = queries.detach().to(device=dev, dtype=torch.float32).contiguous()
+    B = int(q.size(0))
+    uid = None
+    if weights.shape.num_uid_tables > 0:
+        if user_ids is None:
+            raise KeyError("user_ids")  # the reference indexes kwargs["user_ids"] (query_embeddings_fns.py:206)
+        uid = user_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
+    out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+    nbytes = c_size_t()
+    _lib.check(lib.mol_search_workspace_bytes(byref(weights.shape), index.N, B, k, mode, byref(nbytes)))
+    ws = workspace.get(nbytes.value)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.mol_search(
+                byref(weights.shape), byref(weights.struct), byref(index.struct), _ptr(q), _ptr(uid), B, k,
+                1 if sorted else 0, mode, _ptr(out_s), _ptr(out_i), _ptr(ws), ws.numel(), _stream_ptr(dev),
+            )
+        )
+    return out_s, out_i
+
+
+def search_host(
+    weights: PackedWeights,
+    index: IndexHandle,
+    workspace: Workspace,
+    host_queries: torch.Tensor,
+    host_user_ids: Optional[torch.Tensor],
+    k: int,
+    host_out_scores: torch.Tensor,
+    host_out_ids: torch.Tensor,
+    mode: int = _lib.MODE_AUTO,
+) -> None:
+    """mol_search_host: pinned host buffers in/out, copies + sync inside the call (bench.py's e2e leg)."""
+    lib = _lib.load()
+    dev = index.device
+    B = int(host_queries.size(0))
+    assert host_queries.dtype == torch.float32 and host_queries.is_contiguous() and not host_queries.is_cuda
+    nbytes = c_size_t()
+    _lib.check(lib.mol_search_workspace_bytes(byref(weights.shape), index.N, B, k, mode, byref(nbytes)))
+    ws = workspace.get(nbytes.value)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.mol_search_host(
+                byref(weights.shape), byref(weights.struct), byref(index.struct), _ptr(host_queries),
+                _ptr(host_user_ids), B, k, 1, mode, _ptr(host_out_scores), _ptr(host_out_ids), _ptr(ws),
+                ws.numel(), _stream_ptr(dev),
+            )
+        )
+
+
+def score_all(
+    weights: PackedWeights,
+    index: IndexHandle,
+    workspace: Workspace,
+    queries: torch.Tensor,
+    user_ids: Optional[torch.Tensor],
+) -> torch.Tensor:
+    """(B, N) fp32 exact scores (MoLSimilarity.forward, B'==1 branch)."""
+    lib = _lib.load()
+    _require_cuda(queries, "query_embeddings")
+    dev = index.device
+    q = queries.detach().to(device=dev, dtype=torch.float32).contiguous()
+    B = int(q.size(0))
+    uid = None
+    if weights.shape.num_uid_tables > 0:
+        if user_ids is None:
+            raise KeyError("user_ids")
+        uid = user_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
+    out = torch.empty((B, index.N), dtype=torch.float32, device=dev)
+    nbytes = c_size_t()
+    _lib.check(lib.mol_search_workspace_bytes(byref(weights.shape), 1, B, 1, _lib.MODE_EXACT, byref(nbytes)))
+    ws = workspace.get(nbytes.value)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.mol_score_all(
+                byref(weights.shape), byref(weights.struct), byref(index.struct), _ptr(q), _ptr(uid), B,
+                _ptr(out), _ptr(ws), ws.numel(), _stream_ptr(dev),
+            )
+        )
+    return out
+
+
+def query_prologue(
+    weights: PackedWeights, workspace: Workspace, queries: torch.Tensor, user_ids: Optional[torch.Tensor]
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(Q_sub (B, P_Q, d), GQ (B, L)) fp32 from the CUDA query prologue."""
+    lib = _lib.load()
+    _require_cuda(queries, "query_embeddings")
+    dev = queries.device
+    s = weights.shape
+    q = queries.detach().to(dtype=torch.float32).contiguous()
+    B = int(q.size(0))
+    uid = None
+    if s.num_uid_tables > 0:
+        if user_ids is None:
+            raise KeyError("user_ids")
+        uid = user_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
+    L = s.query_dot_product_groups * s.item_dot_product_groups
+    qsub = torch.empty((B, s.query_dot_product_groups, s.dot_product_dimension), dtype=torch.float32, device=dev)
+    gq = torch.empty((B, L), dtype=torch.float32, device=dev)
+    nbytes = c_size_t()
+    _lib.check(lib.mol_search_workspace_bytes(byref(s), 1, B, 1, _lib.MODE_EXACT, byref(nbytes)))
+    ws = workspace.get(nbytes.value)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.mol_query_prologue(
+                byref(s), byref(weights.struct), _ptr(q), _ptr(uid), B, _ptr(qsub), _ptr(gq), _ptr(ws),
+                ws.numel(), _stream_ptr(dev),
+            )
+        )
+    return qsub, gq
+
+
+def merge_topk(part_scores: torch.Tensor, part_ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(R, B, k) per-shard partial top-k -> global (B, k), on the GPU (mol_merge_topk)."""
+    lib = _lib.load()
+    _require_cuda(part_scores, "part_scores")
+    dev = part_scores.device
+    R, B, kk = part_scores.shape
+    assert kk == k and part_ids.shape == part_scores.shape
+    ps = part_scores.detach().to(torch.float32).contiguous()
+    pi = part_ids.detach().to(torch.int64).contiguous()
+    out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+    nbytes = c_size_t()
+    _lib.check(lib.mol_merge_topk_workspace_bytes(R, B, k, byref(nbytes)))
+    ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.mol_merge_topk(_ptr(ps), _ptr(pi), R, B, k, _ptr(out_s), _ptr(out_i), _ptr(ws), ws.numel(), _stream_ptr(dev))
+        )
+    return out_s, out_i
+
+
+def tensor_path_supported(shape: MolShape) -> bool:
+    ok = c_int32(0)
+    _lib.check(_lib.load().mol_shape_check(byref(shape), byref(ok)))
+    return bool(ok.value)
+
+
+def topk(scores: torch.Tensor, k: int, id_map: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Row-wise top-k of a (B, n) fp32 CUDA matrix through mol_topk (sorted, largest first)."""
+    lib = _lib.load()
+    _require_cuda(scores, "scores")
+    assert scores.dim() == 2 and scores.dtype == torch.float32 and scores.stride(1) == 1
+    dev = scores.device
+    B, n = scores.shape
+    out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+    nbytes = c_size_t()
+    _lib.check(lib.mol_topk_workspace_bytes(n, B, k, byref(nbytes)))
+    ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.mol_topk(
+                _ptr(scores), n, scores.stride(0), B, k, _ptr(id_map), _ptr(out_s), _ptr(out_i), _ptr(ws),
+                ws.numel(), _stream_ptr(dev),
+            )
+        )
+    return out_s, out_i

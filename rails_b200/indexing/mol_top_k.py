@@ -1,0 +1,116 @@
+"""Exact brute-force MoL top-k, B200-native drop-in for the reference's
+rails/indexing/mol_top_k.py: `MoLTopKModule` (:29-81) and `MoLBruteForceTopK` (:84-130).
+
+Same constructor, same `forward(query_embeddings, k, sorted=True, **kwargs) -> (scores (B,k),
+ids (B,k) int64)`.  What differs is where the work happens: the item side (projection, l2-norm,
+item-only gating MLP) is computed ONCE into an on-device index at construction (the reference
+recomputes it over the whole corpus on every call), and each forward() is one `mol_search` call of
+libmol_b200.so: CUDA query prologue -> tcgen05 coarse scoring pass (bf16 operands, fp32 accumulate)
+-> radix-select of the K' best per query -> exact fp32 rescoring -> final sorted top-k (+ automatic
+exact fallback for any query whose candidate set cannot be proven complete).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from rails_b200 import _lib, engine
+from rails_b200.indexing.candidate_index import TopKModule
+from rails_b200.similarities.mol.similarity_fn import MoLSimilarity
+
+
+class MoLTopKModule(TopKModule):
+    def __init__(
+        self,
+        mol_module: MoLSimilarity,
+        item_embeddings: torch.Tensor,
+        item_ids: torch.Tensor,
+        flatten_item_ids_and_embeddings: bool,
+        keep_component_level_item_embeddings: bool,
+        component_level_item_embeddings_dtype: torch.dtype = torch.bfloat16,
+    ) -> None:
+        """
+        Args (as in the reference, mol_top_k.py:39-52):
+            mol_module: MoLSimilarity.
+            item_embeddings: (1, X, D) raw item embeddings on a CUDA device.
+            item_ids: (1, X,) item ids.
+        """
+        super().__init__()
+        self._mol_module: MoLSimilarity = mol_module
+        self._item_embeddings: torch.Tensor = (
+            item_embeddings if not flatten_item_ids_and_embeddings else item_embeddings.squeeze(0)
+        )
+        self._item_ids: torch.Tensor = item_ids if not flatten_item_ids_and_embeddings else item_ids.squeeze(0)
+        self._index: Optional[engine.IndexHandle] = None
+        self._index_key = None
+        if keep_component_level_item_embeddings:
+            self._mol_item_embeddings: torch.Tensor = self._ensure_index().xsub_f32().to(
+                component_level_item_embeddings_dtype
+            )
+
+    @property
+    def mol_module(self) -> MoLSimilarity:
+        return self._mol_module
+
+    def _flat_items(self) -> torch.Tensor:
+        e = self._item_embeddings
+        return e.squeeze(0) if e.dim() == 3 else e
+
+    def _ensure_index(self) -> engine.IndexHandle:
+        """(Re)builds the item-side cache when the weights or the item tensor changed."""
+        items = self._flat_items()
+        engine._require_cuda(items, "item_embeddings")
+        weights = self._mol_module.packed_weights(items.device)
+        key = (self._mol_module._packed_key, items.data_ptr(), items._version, tuple(items.shape))
+        if self._index is None or self._index_key != key:
+            self._index = engine.IndexHandle(weights, items, self._item_ids.reshape(-1))
+            self._index_key = key
+        return self._index
+
+
+class MoLBruteForceTopK(MoLTopKModule):
+    def __init__(
+        self,
+        mol_module: MoLSimilarity,
+        item_embeddings: torch.Tensor,
+        item_ids: torch.Tensor,
+        mode: int = _lib.MODE_AUTO,
+    ) -> None:
+        super().__init__(
+            mol_module=mol_module,
+            item_embeddings=item_embeddings,
+            item_ids=item_ids,
+            flatten_item_ids_and_embeddings=False,
+            keep_component_level_item_embeddings=False,
+        )
+        self._mode = mode
+        if item_embeddings.is_cuda:
+            self._ensure_index()
+
+    @torch.no_grad()
+    def forward(
+        self,
+        query_embeddings: torch.Tensor,
+        k: int,
+        sorted: bool = True,
+        **kwargs,
+    ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """
+        Args:
+            query_embeddings: (B, D) x float on the index's CUDA device.
+            k: int. final top-k to return (k <= X, as torch.topk requires; the caller clamps,
+                indexing/candidate_index.py:149 of the reference).
+            sorted: bool. Results are always returned sorted (descending), which satisfies both values.
+            **kwargs: "user_ids" is consumed when uid embeddings are configured; "timestamps" / "ratings"
+                (data/eval.py:148) are accepted and ignored.
+        Returns:
+            Tuple of (top_k_scores x float, top_k_ids x int64), both of shape (B, K,)
+        """
+        index = self._ensure_index()
+        dev = index.device
+        scores, ids = engine.search(
+            self._mol_module.packed_weights(dev), index, self._mol_module.workspace(dev), query_embeddings,
+            kwargs.get("user_ids"), int(k), sorted, self._mode,
+        )
+        return scores.to(query_embeddings.dtype), ids
