@@ -136,6 +136,12 @@ int mol_score_all(const mol_shape_t* shape, const mol_weights_t* w, const mol_in
                   const float* queries, const int64_t* user_ids, int32_t B, float* out_scores,
                   void* workspace, size_t workspace_bytes, mol_stream_t stream);
 
+/* Diagnostic: the (B, N) output of the tcgen05 coarse pass alone (bf16 operands, fp32 accumulation;
+ * approximate — it only ranks candidates for the fp32 rescoring inside mol_search). */
+int mol_score_all_coarse(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
+                         const float* queries, const int64_t* user_ids, int32_t B, float* out_scores,
+                         void* workspace, size_t workspace_bytes, mol_stream_t stream);
+
 /* Query prologue only (query_embeddings_fns.py:175-254 + similarity_fn.py:166-169):
  * out_qsub (B, P_Q, d) fp32 l2-normalised, out_gq (B, L) fp32. */
 int mol_query_prologue(const mol_shape_t* shape, const mol_weights_t* w, const float* queries,

@@ -27,7 +27,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libm
 EXPORTED_SYMBOLS = (
     "mol_version", "mol_last_error", "mol_shape_check", "mol_index_bytes", "mol_index_layout",
     "mol_index_build_workspace_bytes", "mol_index_build", "mol_search_workspace_bytes", "mol_search",
-    "mol_search_host", "mol_score_all", "mol_query_prologue", "mol_merge_topk_workspace_bytes",
+    "mol_search_host", "mol_score_all", "mol_score_all_coarse", "mol_query_prologue", "mol_merge_topk_workspace_bytes",
     "mol_merge_topk", "mol_topk_workspace_bytes", "mol_topk", "mol_launch_count", "mol_launch_count_reset",
     "mol_profile_enable", "mol_profile_collect",
 )
@@ -109,6 +109,7 @@ def load() -> ctypes.CDLL:
     lib.mol_score_all.argtypes = [
         P(MolShape), P(MolWeights), P(MolIndex), c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p,
     ]
+    lib.mol_score_all_coarse.argtypes = lib.mol_score_all.argtypes
     lib.mol_query_prologue.argtypes = [
         P(MolShape), P(MolWeights), c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
     ]

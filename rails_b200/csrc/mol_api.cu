@@ -368,8 +368,12 @@ int mol_index_build(const mol_shape_t* shape, const mol_weights_t* w, const mol_
   // similarity_fn.py:170-171
   MOL_TRY(launch_linear(index->raw_items, w->gi_w1, w->gi_b1, tmp, N, D.Hgi, D.Dx, D.Dx, 1, ACT_SILU, st));
   MOL_TRY(launch_linear(tmp, w->gi_w2, nullptr, index->gi_f32, N, D.L, D.Hgi, D.Hgi, 1, ACT_NONE, st));
-  MOL_TRY(launch_f32_to_bf16(index->gi_f32, reinterpret_cast<__nv_bfloat16*>(index->gi_bf16),
-                             N * D.L, st));
+  if (coarse_supported(*shape)) {
+    MOL_TRY(coarse_gi_image(*shape, index->gi_f32, index->gi_bf16, N, st));
+  } else {
+    MOL_TRY(launch_f32_to_bf16(index->gi_f32, reinterpret_cast<__nv_bfloat16*>(index->gi_bf16),
+                               N * D.L, st));
+  }
   return MOL_OK;
 }
 
@@ -469,6 +473,26 @@ int mol_score_all(const mol_shape_t* shape, const mol_weights_t* w, const mol_in
   MOL_TRY(launch_transpose(w->qi_w2, ws.w2t, D.L, D.H, st));
   return launch_exact_scores(*shape, *w, *index, ws.w1t, ws.w2t, ws.qsub, ws.gq, B, nullptr,
                              index->num_items, index->num_items, out_scores, nullptr, st);
+}
+
+int mol_score_all_coarse(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
+                         const float* queries, const int64_t* user_ids, int32_t B, float* out_scores,
+                         void* workspace, size_t workspace_bytes, mol_stream_t stream) {
+  MOL_TRY(check_shape(shape));
+  MOL_TRY(check_weights(shape, w));
+  MOL_CHECK_ARG(coarse_supported(*shape), "shape not supported by the tensor-core path");
+  MOL_CHECK_ARG(index && index->xsub_bf16 && index->gi_bf16, "index not laid out");
+  MOL_CHECK_ARG(B >= 0, "negative batch");
+  if (B == 0 || index->num_items == 0) return MOL_OK;
+  MOL_CHECK_ARG(queries && out_scores && workspace, "NULL buffer");
+  MOL_CHECK_ARG(shape->num_uid_tables == 0 || user_ids, "user_ids required when uid embeddings are configured");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SearchWs ws;
+  MOL_TRY(plan_search(*shape, /*N=*/1, B, 1, MOL_MODE_TENSOR, workspace, workspace_bytes, &ws));
+  MOL_TRY(run_query_prologue(*shape, *w, queries, user_ids, B, ws.pre, ws.h, ws.proj, ws.hq, ws.qsub,
+                             ws.gq, st));
+  MOL_TRY(coarse_prepare(*shape, *w, ws.coarse, st));
+  return coarse_scores(*shape, *index, ws.coarse, ws.qsub, ws.gq, B, out_scores, st);
 }
 
 int mol_query_prologue(const mol_shape_t* shape, const mol_weights_t* w, const float* queries,

@@ -20,6 +20,8 @@ int coarse_prepare(const mol_shape_t& s, const mol_weights_t& w, const CoarseWs&
 // scores[b, x] ~= MoL score (bf16 operands / fp32 accumulation) for b < bc, x < N; row stride N
 int coarse_scores(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, const float* qsub,
                   const float* gq, int bc, float* scores, cudaStream_t st);
+// gi_bf16 of the index in the kernel's logit order l' = m*P_Q + n (called by the index build)
+int coarse_gi_image(const mol_shape_t& s, const float* gi_f32, uint16_t* gi_bf16, int64_t n, cudaStream_t st);
 // flags[b] = 1 when the coarse candidate set cannot be shown to contain the exact top-k:
 //   cand_scores[b, kk-1] + 1.5 * max_j |cand_scores[b,j] - exact_scores[b,j]| + 1e-3 >= topk_scores[b, k-1]
 int coarse_safety_flags(const float* cand_scores, const float* exact_scores, const float* topk_scores,

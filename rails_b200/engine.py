@@ -220,8 +220,10 @@ def score_all(
     workspace: Workspace,
     queries: torch.Tensor,
     user_ids: Optional[torch.Tensor],
+    coarse: bool = False,
 ) -> torch.Tensor:
-    """(B, N) fp32 exact scores (MoLSimilarity.forward, B'==1 branch)."""
+    """(B, N) fp32 exact scores (MoLSimilarity.forward, B'==1 branch).  coarse=True returns the raw output of
+    the tcgen05 coarse pass instead (diagnostic; approximate)."""
     lib = _lib.load()
     _require_cuda(queries, "query_embeddings")
     dev = index.device
@@ -234,11 +236,13 @@ def score_all(
         uid = user_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
     out = torch.empty((B, index.N), dtype=torch.float32, device=dev)
     nbytes = c_size_t()
-    _lib.check(lib.mol_search_workspace_bytes(byref(weights.shape), 1, B, 1, _lib.MODE_EXACT, byref(nbytes)))
+    mode = _lib.MODE_TENSOR if coarse else _lib.MODE_EXACT
+    _lib.check(lib.mol_search_workspace_bytes(byref(weights.shape), 1, B, 1, mode, byref(nbytes)))
     ws = workspace.get(nbytes.value)
+    fn = lib.mol_score_all_coarse if coarse else lib.mol_score_all
     with torch.cuda.device(dev):
         _lib.check(
-            lib.mol_score_all(
+            fn(
                 byref(weights.shape), byref(weights.struct), byref(index.struct), _ptr(q), _ptr(uid), B,
                 _ptr(out), _ptr(ws), ws.numel(), _stream_ptr(dev),
             )

@@ -205,3 +205,40 @@ def test_full_size_properties_1m_items():
     _, _, sc = O.brute_force_top_k(cfg, sd, q[:1].cpu(), items[sl.to(DEV)].cpu(), ids[sl.to(DEV)].cpu(), k)
     r = O.compare_top_k(s[:1], got[:1], sc, ids[sl.to(DEV)].cpu(), k, SCORE_TOL, TIE_TOL)
     assert r["max_score_err"] <= SCORE_TOL, r
+
+
+# ------------------------------------------------------------------------------- tensor-core coarse pass
+@pytest.mark.parametrize("N,B,seed", [(128, 1, 1), (5000, 7, 2), (40000, 33, 3)])
+def test_coarse_pass_matches_its_numerics_model(N, B, seed):
+    """The raw tcgen05 output against tests/sim_coarse.py (same bf16 rounding points, exact transcendental
+    functions): differences are only accumulation order + tanh.approx/ex2.approx error."""
+    from tests.sim_coarse import coarse_scores
+
+    cfg = CFG_8x8x32
+    mol, _ = build_module(cfg, None, DEV, seed=seed)
+    items, ids, q, _ = synthetic_inputs(cfg, N, B, seed, DEV)
+    w = mol.packed_weights(torch.device(DEV))
+    idx = mol.build_index(items, ids)
+    got = engine.score_all(w, idx, mol.workspace(torch.device(DEV)), q, None, coarse=True).cpu()
+    sd = {k_: v.detach().cpu() for k_, v in mol.state_dict().items()}
+    sim = coarse_scores(cfg, sd, q.cpu(), items.cpu())
+    exact = O.similarity(cfg, sd, q.cpu(), items.cpu())
+    err_sim = (got - sim).abs().max().item()
+    err_exact = (got - exact).abs().max().item()
+    assert torch.isfinite(got).all()
+    assert err_sim < 0.05, (err_sim, err_exact)
+    assert err_exact < 0.35, err_exact
+
+
+def test_coarse_pass_uneven_query_split_and_many_ctas():
+    """bc not a multiple of 2, fewer units than SMs, and a tile range that splits queries across CTAs."""
+    cfg = CFG_8x8x32
+    mol, _ = build_module(cfg, None, DEV, seed=9)
+    dev = torch.device(DEV)
+    for N, B in [(300, 3), (128 * 150, 1), (128 * 37 + 5, 9)]:
+        items, ids, q, _ = synthetic_inputs(cfg, N, B, 11, DEV)
+        idx = mol.build_index(items, ids)
+        w = mol.packed_weights(dev)
+        a = engine.score_all(w, idx, mol.workspace(dev), q, None, coarse=True)
+        e = engine.score_all(w, idx, mol.workspace(dev), q, None)
+        assert (a - e).abs().max().item() < 0.35
