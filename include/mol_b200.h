@@ -89,8 +89,9 @@ typedef struct mol_index {
   const int64_t* item_ids;  /* (N) int64; may be NULL => id == position */
   float* xsub_f32;          /* (N, P_X, d) l2-normalised sub-embeddings  (item_embeddings_fns.py:165-182) */
   float* gi_f32;            /* (N, L)      item-only gating partial      (similarity_fn.py:170-171)       */
-  uint16_t* xsub_bf16;      /* (N_pad, P_X*d) bf16 copy streamed by the tensor-core pass (N_pad = N rounded up to 128; pad rows zero) */
-  uint16_t* gi_bf16;        /* (N_pad, L)  bf16 copy */
+  uint16_t* xsub_half;      /* (N_pad, P_X*d) fp16 copy streamed by the tensor-core pass (N_pad = N rounded up to 128; pad rows zero) */
+  uint16_t* gi_half;        /* (N_pad, L)  fp16 copy, logit order of the tensor-core pass */
+  int32_t* half_overflow;   /* device flag set by the build when a cached value does not fit fp16 (queries then fall back to exact) */
 } mol_index_t;
 
 const char* mol_version(void);
@@ -136,7 +137,7 @@ int mol_score_all(const mol_shape_t* shape, const mol_weights_t* w, const mol_in
                   const float* queries, const int64_t* user_ids, int32_t B, float* out_scores,
                   void* workspace, size_t workspace_bytes, mol_stream_t stream);
 
-/* Diagnostic: the (B, N) output of the tcgen05 coarse pass alone (bf16 operands, fp32 accumulation;
+/* Diagnostic: the (B, N) output of the tcgen05 coarse pass alone (fp16 operands, fp32 accumulation;
  * approximate — it only ranks candidates for the fp32 rescoring inside mol_search). */
 int mol_score_all_coarse(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
                          const float* queries, const int64_t* user_ids, int32_t B, float* out_scores,

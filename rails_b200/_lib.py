@@ -71,8 +71,9 @@ class MolIndex(ctypes.Structure):
         ("item_ids", c_void_p),
         ("xsub_f32", c_void_p),
         ("gi_f32", c_void_p),
-        ("xsub_bf16", c_void_p),
-        ("gi_bf16", c_void_p),
+        ("xsub_half", c_void_p),
+        ("gi_half", c_void_p),
+        ("half_overflow", c_void_p),
     ]
 
 

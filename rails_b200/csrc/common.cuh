@@ -1,6 +1,6 @@
 // Internal helpers shared by the MoL kernels (not part of the C ABI).
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -94,13 +94,12 @@ int launch_linear(const float* A, const float* W, const float* bias, float* C, i
                   int K, int64_t w_sn, int64_t w_sk, Act act, cudaStream_t st);
 // h[b, j] = act(pre[b, j]) * pre[b, Hq + j]   (layers.py:36-43 / 67-74)
 int launch_glu(const float* pre, float* h, int64_t B, int Hq, int kind, cudaStream_t st);
-// rows of `groups` contiguous d-vectors: out = v / max(||v||, eps); optional bf16 copy.
-int launch_l2norm_groups(const float* in, float* out_f32, __nv_bfloat16* out_bf16, int64_t rows,
+// rows of `groups` contiguous d-vectors: out = v / max(||v||, eps); optional fp16 copy.
+int launch_l2norm_groups(const float* in, float* out_f32, __half* out_half, int64_t rows,
                          int groups, int d, float eps, cudaStream_t st);
 // Q_sub assembly: projected groups + uid-embedding groups, then l2 norm (query_embeddings_fns.py:191-253)
 int launch_query_assemble(const mol_shape_t& s, const mol_weights_t& w, const float* proj,
                           const int64_t* user_ids, float* qsub, int B, cudaStream_t st);
-int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t st);
 
 // Exact fp32 scoring.  cand == nullptr: scores[b, x] for x in [0, N) (ld = N).
 // cand != nullptr: scores[b, j] = score(b, cand[b*ld + j]) for j < n_per_query; cand < 0 => -inf.

@@ -76,7 +76,7 @@ static inline int64_t pad128(int64_t n) { return (n + 127) / 128 * 128; }
 
 // ---- index -----------------------------------------------------------------------------------
 struct IndexLayout {
-  size_t xsub_f32, gi_f32, xsub_bf16, gi_bf16, total;
+  size_t xsub_f32, gi_f32, xsub_half, gi_half, half_overflow, total;
 };
 static IndexLayout index_layout(const Dims& D, int64_t N) {
   IndexLayout l;
@@ -89,8 +89,9 @@ static IndexLayout index_layout(const Dims& D, int64_t N) {
   };
   l.xsub_f32 = take((size_t)N * D.Px * D.d * sizeof(float));
   l.gi_f32 = take((size_t)N * D.L * sizeof(float));
-  l.xsub_bf16 = take((size_t)pad128(N) * D.Px * D.d * sizeof(uint16_t));
-  l.gi_bf16 = take((size_t)pad128(N) * D.L * sizeof(uint16_t));
+  l.xsub_half = take((size_t)pad128(N) * D.Px * D.d * sizeof(uint16_t));
+  l.gi_half = take((size_t)pad128(N) * D.L * sizeof(uint16_t));
+  l.half_overflow = take(sizeof(int32_t));
   l.total = align_up(off, 1024);
   return l;
 }
@@ -246,7 +247,8 @@ static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_i
       MOL_TRY(launch_select_final_i32(ws.exact_scores, ws.cand_idx, kk, kk, bc, k, o_scores,
                                       nullptr, o_ids, ix.item_ids, nullptr, st));
       if (kk < N) {
-        MOL_TRY(coarse_safety_flags(ws.cand_scores, ws.exact_scores, o_scores, bc, kk, k, ws.flags, st));
+        MOL_TRY(coarse_safety_flags(ws.cand_scores, ws.exact_scores, o_scores, bc, kk, k, ws.coarse.overflow,
+                                    ix.half_overflow, ws.flags, st));
         // flagged queries are re-done exactly (kernels exit immediately for unflagged rows)
         MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub, gq, bc, nullptr, N, N,
                                     ws.scores, ws.flags, st));
@@ -328,8 +330,9 @@ int mol_index_layout(const mol_shape_t* shape, int64_t num_items, const float* r
   index->item_ids = item_ids;
   index->xsub_f32 = reinterpret_cast<float*>(p + l.xsub_f32);
   index->gi_f32 = reinterpret_cast<float*>(p + l.gi_f32);
-  index->xsub_bf16 = reinterpret_cast<uint16_t*>(p + l.xsub_bf16);
-  index->gi_bf16 = reinterpret_cast<uint16_t*>(p + l.gi_bf16);
+  index->xsub_half = reinterpret_cast<uint16_t*>(p + l.xsub_half);
+  index->gi_half = reinterpret_cast<uint16_t*>(p + l.gi_half);
+  index->half_overflow = reinterpret_cast<int32_t*>(p + l.half_overflow);
   return MOL_OK;
 }
 
@@ -358,21 +361,19 @@ int mol_index_build(const mol_shape_t* shape, const mol_weights_t* w, const mol_
   }
   float* tmp = static_cast<float*>(workspace);
   const int64_t Np = pad128(N);
-  // zero the bf16 pad rows (and everything else) so the tensor-core pass can read whole tiles
-  MOL_CUDA(cudaMemsetAsync(index->xsub_bf16, 0, (size_t)Np * D.Px * D.d * sizeof(uint16_t), st));
-  MOL_CUDA(cudaMemsetAsync(index->gi_bf16, 0, (size_t)Np * D.L * sizeof(uint16_t), st));
+  // zero the fp16 pad rows (and everything else) so the tensor-core pass can read whole tiles
+  MOL_CUDA(cudaMemsetAsync(index->xsub_half, 0, (size_t)Np * D.Px * D.d * sizeof(uint16_t), st));
+  MOL_CUDA(cudaMemsetAsync(index->gi_half, 0, (size_t)Np * D.L * sizeof(uint16_t), st));
+  MOL_CUDA(cudaMemsetAsync(index->half_overflow, 0, sizeof(int32_t), st));
   // item_embeddings_fns.py:165-182
   MOL_TRY(launch_linear(index->raw_items, w->x_w, w->x_b, tmp, N, D.Px * D.d, D.Dx, D.Dx, 1, ACT_NONE, st));
-  MOL_TRY(launch_l2norm_groups(tmp, index->xsub_f32, reinterpret_cast<__nv_bfloat16*>(index->xsub_bf16),
+  MOL_TRY(launch_l2norm_groups(tmp, index->xsub_f32, reinterpret_cast<__half*>(index->xsub_half),
                                N, D.Px, D.d, shape->eps, st));
   // similarity_fn.py:170-171
   MOL_TRY(launch_linear(index->raw_items, w->gi_w1, w->gi_b1, tmp, N, D.Hgi, D.Dx, D.Dx, 1, ACT_SILU, st));
   MOL_TRY(launch_linear(tmp, w->gi_w2, nullptr, index->gi_f32, N, D.L, D.Hgi, D.Hgi, 1, ACT_NONE, st));
   if (coarse_supported(*shape)) {
-    MOL_TRY(coarse_gi_image(*shape, index->gi_f32, index->gi_bf16, N, st));
-  } else {
-    MOL_TRY(launch_f32_to_bf16(index->gi_f32, reinterpret_cast<__nv_bfloat16*>(index->gi_bf16),
-                               N * D.L, st));
+    MOL_TRY(coarse_gi_image(*shape, index->gi_f32, index->gi_half, N, index->half_overflow, st));
   }
   return MOL_OK;
 }
@@ -481,7 +482,7 @@ int mol_score_all_coarse(const mol_shape_t* shape, const mol_weights_t* w, const
   MOL_TRY(check_shape(shape));
   MOL_TRY(check_weights(shape, w));
   MOL_CHECK_ARG(coarse_supported(*shape), "shape not supported by the tensor-core path");
-  MOL_CHECK_ARG(index && index->xsub_bf16 && index->gi_bf16, "index not laid out");
+  MOL_CHECK_ARG(index && index->xsub_half && index->gi_half, "index not laid out");
   MOL_CHECK_ARG(B >= 0, "negative batch");
   if (B == 0 || index->num_items == 0) return MOL_OK;
   MOL_CHECK_ARG(queries && out_scores && workspace, "NULL buffer");

@@ -5,26 +5,41 @@
 namespace mol {
 
 struct CoarseWs {
-  __nv_bfloat16* w1_bf16;  // qi-MLP layer-1 weights in the UMMA shared-memory image (see mol_coarse_sm100.cu)
-  __nv_bfloat16* w2_bf16;  // qi-MLP layer-2 weights, same
-  float* b1h;              // 0.5 * b1   (H)
-  float* b2h;              // 0.5 * b2   (L), permuted to the kernel's logit order
-  __nv_bfloat16* q_bf16;   // (chunk, ...) query sub-embeddings / tau in the UMMA image
-  float* gqh;              // (chunk, L) 0.5 * gq, permuted
+  uint8_t* w1_img;    // qi-MLP layer-1 weights (+ bias column) in the UMMA shared-memory image, fp16
+  uint8_t* w2_img;    // qi-MLP layer-2 weights (+ bias column), same
+  uint8_t* q_rec;     // (chunk, record) per query: block-diagonal image of Q_sub / tau | 0.5 * gq, fp16
+  int32_t* overflow;  // device flag: a weight / query operand did not fit fp16 -> every query falls back to exact
+};
+
+// Where the coarse pass puts its results (any subset).
+struct CoarseOut {
+  float* scores;       // (bc, N) row stride N, or nullptr
+  const float* thr;    // (bc) per-query thresholds of the fused candidate filter, or nullptr
+  int32_t* cand_cnt;   // (bc) counters (zeroed by the caller)
+  float* cand_scores;  // (bc, cand_cap)
+  int32_t* cand_idx;   // (bc, cand_cap)
+  int cand_cap;
 };
 
 bool coarse_supported(const mol_shape_t& s);
 void coarse_plan(const mol_shape_t& s, int chunk, Arena& a, CoarseWs* ws);
 // weight images (once per search call)
 int coarse_prepare(const mol_shape_t& s, const mol_weights_t& w, const CoarseWs& ws, cudaStream_t st);
-// scores[b, x] ~= MoL score (bf16 operands / fp32 accumulation) for b < bc, x < N; row stride N
+// One pass over the corpus for queries [0, bc): fp16 operands / fp32 accumulation scores into `out`.
+int coarse_run(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, const float* qsub, const float* gq,
+               int bc, const CoarseOut& out, cudaStream_t st);
+// scores[b, x] ~= MoL score for b < bc, x < N; row stride N
 int coarse_scores(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, const float* qsub,
                   const float* gq, int bc, float* scores, cudaStream_t st);
-// gi_bf16 of the index in the kernel's logit order l' = m*P_Q + n (called by the index build)
-int coarse_gi_image(const mol_shape_t& s, const float* gi_f32, uint16_t* gi_bf16, int64_t n, cudaStream_t st);
+// gi_half of the index in the kernel's logit order l' = m*P_Q + n (called by the index build); sets *overflow
+// when a value does not fit fp16
+int coarse_gi_image(const mol_shape_t& s, const float* gi_f32, uint16_t* gi_half, int64_t n, int32_t* overflow,
+                    cudaStream_t st);
 // flags[b] = 1 when the coarse candidate set cannot be shown to contain the exact top-k:
 //   cand_scores[b, kk-1] + 1.5 * max_j |cand_scores[b,j] - exact_scores[b,j]| + 1e-3 >= topk_scores[b, k-1]
+// or when either overflow flag is set (operands did not fit fp16).
 int coarse_safety_flags(const float* cand_scores, const float* exact_scores, const float* topk_scores,
-                        int bc, int kk, int k, int32_t* flags, cudaStream_t st);
+                        int bc, int kk, int k, const int32_t* overflow_a, const int32_t* overflow_b,
+                        int32_t* flags, cudaStream_t st);
 
 }  // namespace mol

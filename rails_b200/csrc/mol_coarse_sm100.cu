@@ -1,29 +1,35 @@
-// tcgen05 / TMEM / TMA coarse scoring pass for sm_100a.
+// tcgen05 / TMEM / TMA coarse scoring pass for sm_100a (v2: fp16 operands, everything but the
+// activations on the tensor pipe).
 //
 // Computes, for every (query b, item x) pair, the MoL score of
 //   rails/similarities/mol/similarity_fn.py:389-405 (sub-embedding dot products / tau),
 //   :166-179 (gating: GQ*GI + W2 silu(W1 l + b1) + b2, silu), :42-46 (softmax-weighted sum)
-// with bf16 tensor-core operands and fp32 accumulation, fused in ONE kernel: the (B, N, L) logits,
-// (B, N, H) hidden activations and (B, N, L) gates never leave the SM.  Its (B, N) fp32 output only
-// RANKS candidates; final scores come from the fp32 rescoring pass (mol_exact.cu).
+// with fp16 tensor-core operands and fp32 accumulation, fused in ONE kernel: the (B, N, L) logits,
+// (B, N, H) hidden activations and (B, N, L) gates never leave the SM.  Its output only RANKS
+// candidates; final scores come from the fp32 rescoring pass (mol_exact.cu).
 //
-// Mapping (one persistent CTA per SM, 320 threads):
-//   warp 9      TMA producer : item tile (128 items x P_X*d bf16, SWIZZLE_128B boxes) + the tile's GI rows,
-//                              double-buffered through full/empty mbarriers.
-//   warp 8      MMA issuer   : one elected thread issues every tcgen05.mma and commits to mbarriers.
+// Mapping (one persistent CTA per SM, 352 threads):
 //   warps 0-3   epilogue warpgroup 0  (TMEM slot 0, even queries of the tile's query range)
 //   warps 4-7   epilogue warpgroup 1  (TMEM slot 1, odd queries)
+//   warp 8/9    MMA issuer of slot 0 / slot 1: one thread, blocking mbarrier waits in the slot's fixed order
+//   warp 10     TMA producer: item tile (128 items x P_X*d fp16, SWIZZLE_128B boxes) + the tile's GI rows,
+//               double-buffered through full/empty mbarriers.
 // TMEM lanes = the 128 items of the tile; one epilogue thread owns one (query, item) pair, so every
 // reduction over the L logits is thread-local (no shuffles).  Per query and slot:
-//   G1 (SS): LOG[128 x L]  = X_tile (smem, K = 2d per item-group pair) . Qimg^T   (block-diagonal zero-padded
-//            query image so that N = 16 columns per MMA belong to ONE query; logit order l' = m*P_Q + n)
-//   E1     : LOG -> registers (fp32, kept for the final weighted sum) -> bf16 -> A2 (TMEM, aliases LOG)
-//   G2 (TS): HID[128 x 128] = A2 . (0.5 W1)^T           E2: u = HID + 0.5 b1; h = u + u tanh(u) -> bf16 -> A3 (TMEM)
-//   G3 (TS): GATE[128 x L]  = A3 . (0.5 W2)^T           E3: g = GATE + 0.5 gq*gi + 0.5 b2; w = g + g tanh(g);
-//            online softmax over L in chunks of 16 (ex2.approx), score = sum p*l / sum p -> global.
-// The two warpgroups run independent query pipelines; the MMA thread serves whichever slot is ready, so
-// one group's tensor-core latency hides behind the other group's MUFU/FMA work.
+//   G1 (SS): LOG[128 x L]   = X_tile (smem, K = 2d per item-group pair) . Qimg^T   (block-diagonal zero-padded
+//            query image so that the N = 16 columns of one MMA belong to ONE query; logit order l' = m*P_Q + n)
+//   E1     : LOG -> registers (fp32, kept for the final weighted sum) -> fp16 -> A2 (TMEM, aliases LOG) + a
+//            "ones" K-block that folds the bias b1 into G2
+//   G2 (TS): HID[128 x 128] = [A2 | 1] . [0.5 W1 | 0.5 b1]^T
+//   E2     : u = HID; h = u + u tanh(u) in packed half2 (tanh.approx.f16x2) -> A3 (TMEM) + ones block
+//   G3     : GATE[128 x L]  = GI_tile (smem, SS) . diag(0.5 gq)  +  [A3 | 1] (TS) . [0.5 W2 | 0.5 b2]^T
+//   E3     : u = GATE (= half the gate pre-activation); w = u + u tanh(u); p = 2^(w log2 e) (no max
+//            subtraction: w >= -0.28 and fp32 holds e^w for w < 88; an overflow yields NaN and the
+//            caller's safety check falls back); score = sum p*l / sum p.
+// Output: the (bc, N) score matrix and/or, fused, a per-query threshold filter that appends
+// (score, item) candidates to per-query buffers.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include "mol_coarse.cuh"
@@ -36,8 +42,16 @@ using namespace sm100;
 constexpr int kPQ = 8;          // query groups supported by this kernel
 constexpr int kH = 128;         // gating hidden width
 constexpr int kTile = 128;      // items per tile (= TMEM lanes)
-constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int kThreads = kEpiThreads + 3 * 32;
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kK3 = kH + 16;    // K of the gate GEMM's TS part: hidden units + the ones block
+constexpr int kSmemLimit = 232448;
+
+// TMEM column map of one slot (256 columns)
+constexpr uint32_t kColLog = 0;     // LOG fp32 [0, L); A2 fp16 aliases [0, L/2) + ones [L/2, L/2 + 8)
+constexpr uint32_t kColHid = 64;    // HID fp32 [64, 192); A3 fp16 aliases [64, 128) + ones [128, 136)
+constexpr uint32_t kColGate = 192;  // GATE fp32 [192, 192 + L)
 
 template <int PX, int DD>
 struct CoarseCfg {
@@ -45,38 +59,49 @@ struct CoarseCfg {
   static constexpr int MG = 16 / kPQ;            // item groups per G1 MMA (2)
   static constexpr int K1 = MG * DD;             // K of G1
   static constexpr int NG = PX / MG;             // G1 MMA groups per query
-  static constexpr int XCOLS = PX * DD;          // bf16 per item row
+  static constexpr int K2 = L + 16;              // K of G2: logits + the ones block
+  static constexpr int XCOLS = PX * DD;          // fp16 per item row
   static constexpr int XBOXES = XCOLS / 64;      // 128B-swizzle boxes per tile
   static constexpr int X_BYTES = kTile * XCOLS * 2;
   static constexpr int GI_BYTES = kTile * L * 2;
-  static constexpr int W_BYTES = kH * L * 2;     // both weight images
+  static constexpr int W1_BYTES = kH * K2 * 2;
+  static constexpr int W2_BYTES = L * kK3 * 2;
   static constexpr int Q_BYTES = 16 * K1 * 2;    // query image (16 rows x K1)
-  static constexpr int STAGES = (2 * (X_BYTES + GI_BYTES) + 2 * W_BYTES + 2 * Q_BYTES + 8192 <= 220 * 1024) ? 2 : 1;
-  static constexpr int SMEM_BYTES = STAGES * (X_BYTES + GI_BYTES) + 2 * W_BYTES + 2 * Q_BYTES + 4096 + 1024;
-  static constexpr uint32_t GI_SWIZZLE_MASK = (L == 64) ? 7u : 3u;  // 128B / 64B swizzle
+  static constexpr int QV = Q_BYTES / 16 / 128;  // uint4 per epilogue thread when staging a query image
+  static constexpr int D_BYTES = L * L * 2;      // diag(0.5 gq) image
+  static constexpr int QREC_BYTES = Q_BYTES + L * 2;  // per-query record in global memory: image | 0.5 gq (fp16, l' order)
+  static constexpr int FIXED = W1_BYTES + W2_BYTES + 2 * Q_BYTES + 2 * D_BYTES + 512 /*barriers*/ + 1024 /*alignment*/;
+  static constexpr int STAGES = (2 * (X_BYTES + GI_BYTES) + FIXED <= kSmemLimit) ? 2 : 1;
+  static constexpr int SMEM_BYTES = STAGES * (X_BYTES + GI_BYTES) + FIXED;
+  static_assert(SMEM_BYTES <= kSmemLimit, "shared memory budget exceeded");
+  static_assert(L == 32 || L == 64, "L must be 32 or 64");
+  static_assert(QV >= 1, "query image smaller than one uint4 per thread");
 };
 
 struct CoarseParams {
   const uint8_t* w1_img;
   const uint8_t* w2_img;
-  const float* b1h;
-  const float* b2h;
-  const uint8_t* q_img;  // (bc, Q_BYTES)
-  const float* gqh;      // (bc, L)
-  float* scores;         // (bc, N)
+  const uint8_t* q_rec;   // (bc, QREC_BYTES)
+  float* scores;          // (bc, N) or nullptr
+  // fused candidate filter (all nullptr when unused)
+  const float* thr;       // (bc) per-query threshold
+  int32_t* cand_cnt;      // (bc) running counters
+  float* cand_scores;     // (bc, cand_cap)
+  int32_t* cand_idx;      // (bc, cand_cap)
+  int cand_cap;
   int64_t N;
   int n_tiles;
   int bc;
 };
 
-// canonical no-swizzle K-major UMMA layout of an R x K bf16 matrix (8x8 core matrices, K-adjacent cores contiguous)
+// canonical no-swizzle K-major UMMA layout of an R x K 16-bit matrix (8x8 core matrices, K-adjacent cores contiguous)
 __host__ __device__ inline uint32_t nosw_off(int r, int k, int K) {
   return (uint32_t)((r >> 3) * (K >> 3) * 128 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2);
 }
 
 struct Bars {
   uint64_t full[2], empty[2];
-  uint64_t q_ready[2], a2_ready[2], a3_ready[2];
+  uint64_t q0_ready[2], e1_done[2], e2_done[2];
   uint64_t log_full[2], hid_full[2], gate_full[2];
   uint32_t tmem_base;
 };
@@ -86,7 +111,7 @@ struct TileWalk {
   int64_t f, f1;
   int bc;
   int tile, qa, qb;
-  __device__ TileWalk(int64_t f0_, int64_t f1_, int bc_) : f(f0_), f1(f1_), bc(bc_) {}
+  __device__ TileWalk(int64_t f0_, int64_t f1_, int bc_) : f(f0_), f1(f1_), bc(bc_), tile(0), qa(0), qb(0) {}
   __device__ bool next() {
     if (f >= f1) return false;
     tile = (int)(f / bc);
@@ -96,6 +121,29 @@ struct TileWalk {
     qb = (int)(end - (int64_t)tile * bc);
     f = end;
     return true;
+  }
+  // queries of slot `wg` in the current tile: qa + wg, qa + wg + 2, ...
+  __device__ int n_mine(int wg) const { return (qb - qa + 1 - wg) / 2; }
+};
+
+// The flattened (tile, query) sequence of one slot.
+struct SlotSeq {
+  TileWalk w;
+  int wg, q;
+  bool in_tile;
+  __device__ SlotSeq(int64_t f0, int64_t f1, int bc, int wg_) : w(f0, f1, bc), wg(wg_), q(0), in_tile(false) {}
+  __device__ bool next(int& tile, int& query) {
+    while (true) {
+      if (in_tile && q < w.qb) {
+        tile = w.tile;
+        query = q;
+        q += 2;
+        return true;
+      }
+      if (!w.next()) return false;
+      q = w.qa + wg;
+      in_tile = true;
+    }
   }
 };
 
@@ -109,30 +157,27 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sX = smem;                                   // STAGES x X_BYTES   (1024-aligned boxes)
   unsigned char* sGI = sX + C::STAGES * C::X_BYTES;           // STAGES x GI_BYTES
-  unsigned char* sW1 = sGI + C::STAGES * C::GI_BYTES;         // 128 x L  (no-swizzle image)
-  unsigned char* sW2 = sW1 + C::W_BYTES;                      // L x 128
-  unsigned char* sQ = sW2 + C::W_BYTES;                       // 2 x Q_BYTES
-  float* sB1 = reinterpret_cast<float*>(sQ + 2 * C::Q_BYTES);  // 128
-  float* sB2 = sB1 + kH;                                      // L
-  float* sGQ = sB2 + L;                                       // 2 slots x 2 buffers x L
-  Bars* bars = reinterpret_cast<Bars*>(sGQ + 4 * L);
+  unsigned char* sW1 = sGI + C::STAGES * C::GI_BYTES;         // 128 x K2  (no-swizzle image)
+  unsigned char* sW2 = sW1 + C::W1_BYTES;                     // L x 144
+  unsigned char* sQ = sW2 + C::W2_BYTES;                      // 2 x Q_BYTES
+  unsigned char* sD = sQ + 2 * C::Q_BYTES;                    // 2 x D_BYTES
+  Bars* bars = reinterpret_cast<Bars*>(sD + 2 * C::D_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup
-  for (int i = tid; i < C::W_BYTES / 16; i += kThreads) {
+  for (int i = tid; i < C::W1_BYTES / 16; i += kThreads)
     reinterpret_cast<uint4*>(sW1)[i] = reinterpret_cast<const uint4*>(P.w1_img)[i];
+  for (int i = tid; i < C::W2_BYTES / 16; i += kThreads)
     reinterpret_cast<uint4*>(sW2)[i] = reinterpret_cast<const uint4*>(P.w2_img)[i];
-  }
-  for (int i = tid; i < kH; i += kThreads) sB1[i] = P.b1h[i];
-  for (int i = tid; i < L; i += kThreads) sB2[i] = P.b2h[i];
+  for (int i = tid; i < 2 * C::D_BYTES / 16; i += kThreads) reinterpret_cast<uint4*>(sD)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], 256);
-      mbar_init(&bars->q_ready[s], 128);
-      mbar_init(&bars->a2_ready[s], 128);
-      mbar_init(&bars->a3_ready[s], 128);
+      mbar_init(&bars->empty[s], 2);
+      mbar_init(&bars->q0_ready[s], 128);
+      mbar_init(&bars->e1_done[s], 128);
+      mbar_init(&bars->e2_done[s], 128);
       mbar_init(&bars->log_full[s], 1);
       mbar_init(&bars->hid_full[s], 1);
       mbar_init(&bars->gate_full[s], 1);
@@ -140,7 +185,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc<512>(&bars->tmem_base);
-  if (warp == 9 && lane == 0) {
+  if (warp == 10 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmGI);
   }
@@ -154,7 +199,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int64_t F = (int64_t)P.n_tiles * P.bc;
   const int64_t f0 = F * blockIdx.x / gridDim.x, f1 = F * (blockIdx.x + 1) / gridDim.x;
 
-  if (warp == 9) {
+  if (warp == 10) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       TileWalk w(f0, f1, P.bc);
@@ -162,7 +207,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       while (w.next()) {
         const int s = it % C::STAGES;
         const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-        mbar_wait(&bars->empty[s], ph ^ 1u);
+        mbar_wait_sleep(&bars->empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&bars->full[s], C::X_BYTES + C::GI_BYTES);
 #pragma unroll
         for (int bx = 0; bx < C::XBOXES; ++bx)
@@ -171,70 +216,101 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ++it;
       }
     }
-  } else if (warp == 8) {
-    // =============================== MMA issuer ===============================
+  } else if (warp >= 8) {
+    // =============================== MMA issuer of slot `wg` ===============================
     if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_bf16(128, 16);
-      constexpr uint32_t idesc2 = make_idesc_bf16(128, kH);
-      constexpr uint32_t idesc3 = make_idesc_bf16(128, L);
+      const int wg = warp - 8;
+      constexpr uint32_t idesc1 = make_idesc_f16(128, 16);
+      constexpr uint32_t idesc2 = make_idesc_f16(128, kH);
+      constexpr uint32_t idesc3 = make_idesc_f16(128, L);
       const uint32_t sW1a = smem_u32(sW1), sW2a = smem_u32(sW2);
-      uint32_t cnt[2] = {0, 0};  // queries fully issued (G1) per slot since kernel start -> barrier parity
-      uint32_t c2[2] = {0, 0}, c3[2] = {0, 0};
-      TileWalk w(f0, f1, P.bc);
-      int it = 0;
-      while (w.next()) {
-        const int s = it % C::STAGES;
-        mbar_wait(&bars->full[s], (uint32_t)(it / C::STAGES) & 1u);
-        tc_fence_after();
+      const uint32_t sQa = smem_u32(sQ + wg * C::Q_BYTES), sDa = smem_u32(sD + wg * C::D_BYTES);
+      const uint32_t base = tmem + (uint32_t)wg * 256u;
+      uint32_t c1 = 0, c2 = 0;  // completed e1_done / e2_done phases of this slot
+      bool first = true, pre_g1 = false;
+
+      auto issue_g1 = [&](int s) {
         const uint32_t sXa = smem_u32(sX + s * C::X_BYTES);
-        const int nq = w.qb - w.qa;
-        const int n[2] = {(nq + 1) / 2, nq / 2};
-        int g1[2] = {0, 0}, g2[2] = {0, 0}, g3[2] = {0, 0};
-        while (g3[0] < n[0] || g3[1] < n[1]) {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const uint32_t base = tmem + (uint32_t)i * 256u;
-            if (g1[i] < n[i] && g1[i] == g2[i] && mbar_try_wait(&bars->q_ready[i], cnt[i] & 1u)) {
-              tc_fence_after();
-              const uint32_t sQa = smem_u32(sQ + i * C::Q_BYTES);
+        for (int g = 0; g < C::NG; ++g) {
 #pragma unroll
-              for (int g = 0; g < C::NG; ++g) {
-#pragma unroll
-                for (int ks = 0; ks < C::K1 / 16; ++ks) {
-                  const int e = g * C::K1 + ks * 16;  // first bf16 column of this K step in the item row
-                  const uint64_t da = make_smem_desc(sXa + (e / 64) * 16384 + (e % 64) * 2, 16, 1024, 2);
-                  const uint64_t db = make_smem_desc(sQa + ks * 256, 128, (C::K1 / 8) * 128, 0);
-                  umma_ss(base + g * 16, da, db, idesc1, ks > 0);
-                }
-              }
-              umma_commit(&bars->log_full[i]);
-              ++g1[i];
-              ++cnt[i];
-            }
-            if (g2[i] < g1[i] && mbar_try_wait(&bars->a2_ready[i], c2[i] & 1u)) {
-              tc_fence_after();
-#pragma unroll
-              for (int ks = 0; ks < L / 16; ++ks) {
-                const uint64_t db = make_smem_desc(sW1a + ks * 256, 128, (L / 8) * 128, 0);
-                umma_ts(base + 64, base + ks * 8, db, idesc2, ks > 0);
-              }
-              umma_commit(&bars->hid_full[i]);
-              ++g2[i];
-              ++c2[i];
-            }
-            if (g3[i] < g2[i] && mbar_try_wait(&bars->a3_ready[i], c3[i] & 1u)) {
-              tc_fence_after();
-#pragma unroll
-              for (int ks = 0; ks < kH / 16; ++ks) {
-                const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kH / 8) * 128, 0);
-                umma_ts(base + 128, base + 64 + ks * 8, db, idesc3, ks > 0);
-              }
-              umma_commit(&bars->gate_full[i]);
-              ++g3[i];
-              ++c3[i];
-            }
+          for (int ks = 0; ks < C::K1 / 16; ++ks) {
+            const int e = g * C::K1 + ks * 16;  // first fp16 column of this K step in the item row
+            const uint64_t da = make_smem_desc(sXa + (e / 64) * 16384 + (e % 64) * 2, 16, 1024, 2);
+            const uint64_t db = make_smem_desc(sQa + ks * 256, 128, (C::K1 / 8) * 128, 0);
+            umma_ss(base + kColLog + g * 16, da, db, idesc1, ks > 0);
           }
         }
+        umma_commit(&bars->log_full[wg]);
+      };
+
+      TileWalk w(f0, f1, P.bc);
+      int it = 0;
+      bool have = w.next();
+      while (have) {
+        const int s = it % C::STAGES;
+        mbar_wait_sleep(&bars->full[s], (uint32_t)(it / C::STAGES) & 1u);
+        tc_fence_after();
+        const int n = w.n_mine(wg);
+        // look ahead: the next tile of this CTA (its first query's G1 is issued early, behind the last G2 of this tile)
+        TileWalk wn = w;
+        const bool have_next = wn.next();
+        const int n_next = have_next ? wn.n_mine(wg) : 0;
+        if (n == 0) {
+          mbar_arrive(&bars->empty[s]);
+        } else {
+          if (!pre_g1) {
+            if (first) {
+              mbar_wait_sleep(&bars->q0_ready[wg], 0);
+              tc_fence_after();
+            }
+            issue_g1(s);
+          }
+          first = false;
+          pre_g1 = false;
+          const uint32_t sGIa = smem_u32(sGI + s * C::GI_BYTES);
+          for (int j = 0; j < n; ++j) {
+            // ---- G2 (+ the next query's G1) once E1 has written A2 and staged the next query image
+            mbar_wait_sleep(&bars->e1_done[wg], c1 & 1u);
+            ++c1;
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < C::K2 / 16; ++ks) {
+              const uint64_t db = make_smem_desc(sW1a + ks * 256, 128, (C::K2 / 8) * 128, 0);
+              umma_ts(base + kColHid, base + kColLog + ks * 8, db, idesc2, ks > 0);
+            }
+            umma_commit(&bars->hid_full[wg]);
+            if (j + 1 < n) {
+              issue_g1(s);
+            } else if (n_next > 0 && C::STAGES > 1) {  // (single stage: the next tile cannot land before this one is released)
+              const int sn = (it + 1) % C::STAGES;
+              mbar_wait_sleep(&bars->full[sn], (uint32_t)((it + 1) / C::STAGES) & 1u);
+              tc_fence_after();
+              issue_g1(sn);
+              pre_g1 = true;
+            }
+            // ---- G3 once E2 has written A3
+            mbar_wait_sleep(&bars->e2_done[wg], c2 & 1u);
+            ++c2;
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < L / 16; ++ks) {  // GATE = GI_tile . diag(0.5 gq)
+              const uint64_t da = (L == 64) ? make_smem_desc(sGIa + ks * 32, 16, 1024, 2)
+                                            : make_smem_desc(sGIa + ks * 32, 16, 512, 4);
+              const uint64_t db = make_smem_desc(sDa + ks * 256, 128, (L / 8) * 128, 0);
+              umma_ss(base + kColGate, da, db, idesc3, ks > 0);
+            }
+#pragma unroll
+            for (int ks = 0; ks < kK3 / 16; ++ks) {  // += [A3 | 1] . [0.5 W2 | 0.5 b2]^T
+              const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
+              umma_ts(base + kColGate, base + kColHid + ks * 8, db, idesc3, 1u);
+            }
+            umma_commit(&bars->gate_full[wg]);
+            if (j == n - 1) umma_commit(&bars->empty[s]);  // every MMA of this slot that reads stage s is issued
+          }
+        }
+        w = wn;
+        have = have_next;
         ++it;
       }
     }
@@ -245,123 +321,163 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t base = tmem + (uint32_t)wg * 256u + lane_base;
     unsigned char* sQw = sQ + wg * C::Q_BYTES;
-    uint32_t cnt = 0;  // queries processed by this slot
-    TileWalk w(f0, f1, P.bc);
-    int it = 0;
-    while (w.next()) {
-      const int s = it % C::STAGES;
-      mbar_wait(&bars->full[s], (uint32_t)(it / C::STAGES) & 1u);
-      const unsigned char* gi_row = sGI + s * C::GI_BYTES + r * (L * 2);
-      const int64_t item = (int64_t)w.tile * kTile + r;
-      const int nq = w.qb - w.qa;
-      const int n_mine = wg == 0 ? (nq + 1) / 2 : nq / 2;
+    __half* sDw = reinterpret_cast<__half*>(sD + wg * C::D_BYTES + (r < L ? nosw_off(r, r, L) : 0));
+    uint32_t cnt = 0;  // queries processed by this slot -> barrier parity
 
-      auto stage_query = [&](int q, uint32_t buf) {
-        const uint4* src = reinterpret_cast<const uint4*>(P.q_img + (size_t)q * C::Q_BYTES);
+    // prefetched query data: image of the NEXT query to stage, 0.5*gq[r] of the query whose diag is staged next
+    uint4 qv[C::QV];
+    __half gqv = __float2half(0.f);
+    auto load_image = [&](int q) {
+      const uint4* src = reinterpret_cast<const uint4*>(P.q_rec + (size_t)q * C::QREC_BYTES);
 #pragma unroll
-        for (int i = 0; i < C::Q_BYTES / 16 / 128; ++i) reinterpret_cast<uint4*>(sQw)[r + i * 128] = src[r + i * 128];
-        if (r < L / 4)
-          reinterpret_cast<float4*>(sGQ + (wg * 2 + buf) * L)[r] = reinterpret_cast<const float4*>(P.gqh + (size_t)q * L)[r];
-        fence_proxy_async_smem();
-        mbar_arrive(&bars->q_ready[wg]);
-      };
+      for (int i = 0; i < C::QV; ++i) qv[i] = __ldg(src + r + i * 128);
+    };
+    auto load_gq = [&](int q) {
+      if (r < L) gqv = reinterpret_cast<const __half*>(P.q_rec + (size_t)q * C::QREC_BYTES + C::Q_BYTES)[r];
+    };
+    auto store_image = [&]() {
+#pragma unroll
+      for (int i = 0; i < C::QV; ++i) reinterpret_cast<uint4*>(sQw)[r + i * 128] = qv[i];
+    };
 
-      if (n_mine > 0) stage_query(w.qa + wg, cnt & 1u);
-      for (int j = 0; j < n_mine; ++j) {
-        const int q = w.qa + wg + 2 * j;
-        const uint32_t par = cnt & 1u;
-        // ---------------- E1: logits -> registers, bf16 copy -> A2
-        mbar_wait(&bars->log_full[wg], par);
-        tc_fence_after();
-        uint32_t lg[L];
+    SlotSeq seq(f0, f1, P.bc, wg);
+    int tile = 0, q = 0, tile_n = 0, q_n = 0;
+    bool have = seq.next(tile, q);
+    if (have) {
+      load_image(q);
+      load_gq(q);
+      store_image();
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->q0_ready[wg]);
+    }
+    bool have_n = have && seq.next(tile_n, q_n);
+    if (have_n) load_image(q_n);
+
+    uint32_t ones[8];
+    ones[0] = 0x00003C00u;  // {1.0h, 0}
 #pragma unroll
-        for (int c = 0; c < L; c += 32) tmem_ld_x32(base + c, lg + c);
-        tmem_ld_wait();
-        {
-          uint32_t pk[L / 2];
+    for (int i = 1; i < 8; ++i) ones[i] = 0u;
+    const float2 l2e2 = make_float2(kLog2e, kLog2e);
+
+    while (have) {
+      const uint32_t par = cnt & 1u;
+      // ---------------- E1: logits -> registers, fp16 copy -> A2; stage next query image + this query's diag
+      mbar_wait_sleep(&bars->log_full[wg], par);
+      tc_fence_after();
+      uint32_t lg[L];
 #pragma unroll
-          for (int j2 = 0; j2 < L / 2; ++j2)
-            pk[j2] = pack_bf16x2(__uint_as_float(lg[2 * j2]), __uint_as_float(lg[2 * j2 + 1]));
+      for (int c = 0; c < L; c += 32) tmem_ld_x32(base + kColLog + c, lg + c);
+      // G1 of this query is complete: its image buffer is free; G3 of the previous query completed before the
+      // previous E3: the diag buffer is free.
+      if (have_n) store_image();
+      if (r < L) *sDw = gqv;
+      fence_proxy_async_smem();
+      tmem_ld_wait_bind32(lg);
+      if constexpr (L == 64) tmem_ld_wait_bind32(lg + 32);
+      {
+        uint32_t pk[L / 2];
 #pragma unroll
-          for (int c = 0; c < L / 2; c += 16) tmem_st_x16(base + c, pk + c);
+        for (int j2 = 0; j2 < L / 2; ++j2)
+          pk[j2] = pack_f16x2(__uint_as_float(lg[2 * j2]), __uint_as_float(lg[2 * j2 + 1]));
+        if constexpr (L == 64) {
+          tmem_st_x32(base + kColLog, pk);
+        } else {
+          tmem_st_x16(base + kColLog, pk);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bars->a2_ready[wg]);
-        if (j + 1 < n_mine) stage_query(q + 2, (cnt + 1) & 1u);
+        tmem_st_x8(base + kColLog + L / 2, ones);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bars->e1_done[wg]);
+      // prefetch: gq of the next query, image of the one after
+      int tile_nn = 0, q_nn = 0;
+      const bool have_nn = have_n && seq.next(tile_nn, q_nn);
+      if (have_n) load_gq(q_n);
+      if (have_nn) load_image(q_nn);
 
-        // ---------------- E2: hidden activations -> bf16 -> A3 (in place, first half of HID)
-        mbar_wait(&bars->hid_full[wg], par);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld_x32(base + 64 + 32 * c, v);
-          tmem_ld_wait();
+      // ---------------- E2: hidden activations (packed half2) -> A3 (in place, first half of HID) + ones block
+      mbar_wait_sleep(&bars->hid_full[wg], par);
+      tc_fence_after();
+      {
+        uint32_t va[32], vb[32];
+        auto act = [&](const uint32_t* v, uint32_t col) {
           uint32_t pk[16];
 #pragma unroll
           for (int j2 = 0; j2 < 16; ++j2) {
-            const float2 bb = *reinterpret_cast<const float2*>(sB1 + 32 * c + 2 * j2);
-            const float u0 = __uint_as_float(v[2 * j2]) + bb.x;
-            const float u1 = __uint_as_float(v[2 * j2 + 1]) + bb.y;
-            const float h0 = fmaf(u0, tanh_approx(u0), u0);
-            const float h1 = fmaf(u1, tanh_approx(u1), u1);
-            pk[j2] = pack_bf16x2(h0, h1);
+            const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+            pk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
           }
-          tmem_st_x16(base + 64 + 16 * c, pk);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bars->a3_ready[wg]);
+          tmem_st_x16(base + col, pk);
+        };
+        tmem_ld_x32(base + kColHid, va);
+        tmem_ld_wait_bind32(va);
+        tmem_ld_x32(base + kColHid + 32, vb);
+        act(va, kColHid);
+        tmem_ld_wait_bind32(vb);
+        tmem_ld_x32(base + kColHid + 64, va);
+        act(vb, kColHid + 16);
+        tmem_ld_wait_bind32(va);
+        tmem_ld_x32(base + kColHid + 96, vb);
+        act(va, kColHid + 32);
+        tmem_ld_wait_bind32(vb);
+        act(vb, kColHid + 48);
+        tmem_st_x8(base + kColHid + 64, ones);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bars->e2_done[wg]);
 
-        // ---------------- E3: gate -> silu -> online softmax -> weighted sum
-        mbar_wait(&bars->gate_full[wg], par);
-        tc_fence_after();
-        const float* gq = sGQ + (wg * 2 + par) * L;
-        float M = -CUDART_INF_F, num = 0.f, den = 0.f;
+      // ---------------- E3: gate -> silu -> softmax (no max subtraction) -> weighted sum
+      mbar_wait_sleep(&bars->gate_full[wg], par);
+      tc_fence_after();
+      float2 num[4], den[4];
 #pragma unroll
-        for (int c = 0; c < L / 16; ++c) {
-          uint32_t v[16];
-          tmem_ld_x16(base + 128 + 16 * c, v);
-          // GI row chunk pair (2c, 2c+1), undoing the TMA swizzle (16-byte chunk index XOR row bits)
-          const uint32_t sw = (L == 64) ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
-          const uint4 ga = *reinterpret_cast<const uint4*>(gi_row + (((uint32_t)(2 * c) ^ sw) << 4));
-          const uint4 gb = *reinterpret_cast<const uint4*>(gi_row + (((uint32_t)(2 * c + 1) ^ sw) << 4));
-          const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-          tmem_ld_wait();
-          float wv[16];
-          float mc = -CUDART_INF_F;
-#pragma unroll
-          for (int j2 = 0; j2 < 8; ++j2) {
-            const float gi0 = __uint_as_float(gw[j2] << 16);
-            const float gi1 = __uint_as_float(gw[j2] & 0xffff0000u);
-            const float2 gqv = *reinterpret_cast<const float2*>(gq + 16 * c + 2 * j2);
-            const float2 b2v = *reinterpret_cast<const float2*>(sB2 + 16 * c + 2 * j2);
-            const float u0 = fmaf(gqv.x, gi0, __uint_as_float(v[2 * j2])) + b2v.x;
-            const float u1 = fmaf(gqv.y, gi1, __uint_as_float(v[2 * j2 + 1])) + b2v.y;
-            wv[2 * j2] = fmaf(u0, tanh_approx(u0), u0);
-            wv[2 * j2 + 1] = fmaf(u1, tanh_approx(u1), u1);
-            mc = fmaxf(mc, fmaxf(wv[2 * j2], wv[2 * j2 + 1]));
-          }
-          const float Mn = fmaxf(M, mc);
-          const float sc = ex2_approx((M - Mn) * kLog2e);
-          num *= sc;
-          den *= sc;
-          M = Mn;
-          const float off = -Mn * kLog2e;
+      for (int i = 0; i < 4; ++i) num[i] = den[i] = make_float2(0.f, 0.f);
+      {
+        uint32_t va[32], vb[32];
+        auto gate = [&](const uint32_t* v, const uint32_t* lgc) {
 #pragma unroll
           for (int j2 = 0; j2 < 16; ++j2) {
-            const float e = ex2_approx(fmaf(wv[j2], kLog2e, off));
-            den += e;
-            num = fmaf(e, __uint_as_float(lg[16 * c + j2]), num);
+            const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+            const float2 a = __fmul2_rn(u, l2e2);
+            const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+            const float2 x = __ffma2_rn(a, t, a);
+            const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            den[j2 & 3] = __fadd2_rn(den[j2 & 3], e);
+            num[j2 & 3] = __ffma2_rn(e, make_float2(__uint_as_float(lgc[2 * j2]), __uint_as_float(lgc[2 * j2 + 1])),
+                                     num[j2 & 3]);
+          }
+        };
+        tmem_ld_x32(base + kColGate, va);
+        tmem_ld_wait_bind32(va);
+        if constexpr (L == 64) tmem_ld_x32(base + kColGate + 32, vb);
+        gate(va, lg);
+        if constexpr (L == 64) {
+          tmem_ld_wait_bind32(vb);
+          gate(vb, lg + 32);
+        }
+      }
+      const float2 n2 = __fadd2_rn(__fadd2_rn(num[0], num[1]), __fadd2_rn(num[2], num[3]));
+      const float2 d2 = __fadd2_rn(__fadd2_rn(den[0], den[1]), __fadd2_rn(den[2], den[3]));
+      const float score = __fdividef(n2.x + n2.y, d2.x + d2.y);
+      const int64_t item = (int64_t)tile * kTile + r;
+      if (item < P.N) {
+        if (P.scores) P.scores[(size_t)q * P.N + item] = score;
+        if (P.thr && !(score < __ldg(P.thr + q))) {  // NaN passes the filter on purpose
+          const int pos = atomicAdd(P.cand_cnt + q, 1);
+          if (pos < P.cand_cap) {
+            P.cand_scores[(size_t)q * P.cand_cap + pos] = score;
+            P.cand_idx[(size_t)q * P.cand_cap + pos] = (int32_t)item;
           }
         }
-        if (item < P.N) P.scores[(size_t)q * P.N + item] = __fdividef(num, den);
-        ++cnt;
       }
-      // this warpgroup is done with the tile's smem (GI rows; X was last read by a G1 that completed before E1)
-      mbar_arrive(&bars->empty[s]);
-      ++it;
+      ++cnt;
+      tile = tile_n;
+      q = q_n;
+      have = have_n;
+      tile_n = tile_nn;
+      q_n = q_nn;
+      have_n = have_nn;
     }
   }
 
@@ -376,63 +492,72 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 // logit order of the kernel: l' = m*PQ + n  <->  reference l = n*PX + m
 __device__ __forceinline__ int ref_l(int lp, int PQ, int PX) { return (lp % PQ) * PX + (lp / PQ); }
 
-__global__ void coarse_weight_images_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
-                                            const float* __restrict__ w2, const float* __restrict__ b2,
-                                            uint8_t* w1_img, uint8_t* w2_img, float* b1h, float* b2h, int PQ,
-                                            int PX) {
-  const int L = PQ * PX;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < kH * L) {
-    {  // W1 image: rows h (N = 128), K = L (l')
-      const int h = i / L, lp = i % L;
-      const float v = 0.5f * w1[h * L + ref_l(lp, PQ, PX)];
-      *reinterpret_cast<__nv_bfloat16*>(w1_img + nosw_off(h, lp, L)) = __float2bfloat16_rn(v);
-    }
-    {  // W2 image: rows l' (N = L), K = 128
-      const int lp = i / kH, h = i % kH;
-      const float v = 0.5f * w2[ref_l(lp, PQ, PX) * kH + h];
-      *reinterpret_cast<__nv_bfloat16*>(w2_img + nosw_off(lp, h, kH)) = __float2bfloat16_rn(v);
-    }
-  }
-  if (i < kH) b1h[i] = 0.5f * b1[i];
-  if (i < L) b2h[i] = 0.5f * b2[ref_l(i, PQ, PX)];
+__device__ __forceinline__ __half to_half_checked(float v, int32_t* overflow) {
+  if (!(fabsf(v) <= 65504.f)) atomicOr(overflow, 1);
+  return __float2half_rn(v);
 }
 
-// Per query: block-diagonal zero-padded image of Q_sub / tau (16 rows x K1) and the permuted 0.5*gq.
-__global__ void coarse_query_images_kernel(const float* __restrict__ qsub, const float* __restrict__ gq,
-                                           uint8_t* q_img, float* gqh, int bc, int PQ, int PX, int d,
-                                           float inv_tau) {
+// W1 image: rows h (N = 128), K = L + 16: [0.5 W1 (l' order) | 0.5 b1 | 0...].
+// W2 image: rows l' (N = L), K = 144:     [0.5 W2           | 0.5 b2 | 0...].
+__global__ void coarse_weight_images_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
+                                            const float* __restrict__ w2, const float* __restrict__ b2,
+                                            uint8_t* w1_img, uint8_t* w2_img, int32_t* overflow, int PQ, int PX) {
+  const int L = PQ * PX, K2 = L + 16;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kH * K2) {
+    const int h = i / K2, k = i % K2;
+    float v = 0.f;
+    if (k < L) v = 0.5f * w1[h * L + ref_l(k, PQ, PX)];
+    else if (k == L) v = 0.5f * b1[h];
+    *reinterpret_cast<__half*>(w1_img + nosw_off(h, k, K2)) = to_half_checked(v, overflow);
+  }
+  if (i < L * kK3) {
+    const int lp = i / kK3, k = i % kK3;
+    float v = 0.f;
+    if (k < kH) v = 0.5f * w2[ref_l(lp, PQ, PX) * kH + k];
+    else if (k == kH) v = 0.5f * b2[ref_l(lp, PQ, PX)];
+    *reinterpret_cast<__half*>(w2_img + nosw_off(lp, k, kK3)) = to_half_checked(v, overflow);
+  }
+}
+
+// Per query record: block-diagonal zero-padded image of Q_sub / tau (16 rows x K1) followed by 0.5*gq (fp16, l' order).
+__global__ void coarse_query_records_kernel(const float* __restrict__ qsub, const float* __restrict__ gq,
+                                            uint8_t* q_rec, int32_t* overflow, int bc, int PQ, int PX, int d,
+                                            float inv_tau) {
   const int MG = 16 / PQ, K1 = MG * d, L = PQ * PX;
   const int q = blockIdx.x;
   if (q >= bc) return;
-  uint8_t* img = q_img + (size_t)q * 16 * K1 * 2;
+  uint8_t* rec = q_rec + (size_t)q * (16 * K1 * 2 + L * 2);
   for (int i = threadIdx.x; i < 16 * K1; i += blockDim.x) {
     const int row = i / K1, k = i % K1;
     const int mm = row / PQ, n = row % PQ;
     float v = 0.f;
     if (k / d == mm) v = qsub[((size_t)q * PQ + n) * d + (k % d)] * inv_tau;
-    *reinterpret_cast<__nv_bfloat16*>(img + nosw_off(row, k, K1)) = __float2bfloat16_rn(v);
+    *reinterpret_cast<__half*>(rec + nosw_off(row, k, K1)) = to_half_checked(v, overflow);
   }
-  for (int lp = threadIdx.x; lp < L; lp += blockDim.x) gqh[(size_t)q * L + lp] = 0.5f * gq[(size_t)q * L + ref_l(lp, PQ, PX)];
+  __half* g = reinterpret_cast<__half*>(rec + 16 * K1 * 2);
+  for (int lp = threadIdx.x; lp < L; lp += blockDim.x)
+    g[lp] = to_half_checked(0.5f * gq[(size_t)q * L + ref_l(lp, PQ, PX)], overflow);
 }
 
-// gi_bf16 in the index is stored in the kernel's logit order (written by the index build through this kernel)
-__global__ void coarse_gi_image_kernel(const float* __restrict__ gi, __nv_bfloat16* __restrict__ out, int64_t n,
-                                       int PQ, int PX) {
+// gi_half of the index in the kernel's logit order (written by the index build through this kernel)
+__global__ void coarse_gi_image_kernel(const float* __restrict__ gi, __half* __restrict__ out, int64_t n,
+                                       int32_t* overflow, int PQ, int PX) {
   const int L = PQ * PX;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * L) return;
   const int64_t x = i / L;
   const int lp = (int)(i % L);
-  out[i] = __float2bfloat16_rn(gi[x * L + ref_l(lp, PQ, PX)]);
+  out[i] = to_half_checked(gi[x * L + ref_l(lp, PQ, PX)], overflow);
 }
 
-int coarse_gi_image(const mol_shape_t& s, const float* gi_f32, uint16_t* gi_bf16, int64_t n, cudaStream_t st) {
+int coarse_gi_image(const mol_shape_t& s, const float* gi_f32, uint16_t* gi_half, int64_t n, int32_t* overflow,
+                    cudaStream_t st) {
   Dims D = dims_of(s);
   if (n == 0) return MOL_OK;
   const int64_t total = n * D.L;
-  coarse_gi_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      gi_f32, reinterpret_cast<__nv_bfloat16*>(gi_bf16), n, D.Pq, D.Px);
+  coarse_gi_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gi_f32, reinterpret_cast<__half*>(gi_half),
+                                                                          n, overflow, D.Pq, D.Px);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
 }
@@ -444,26 +569,26 @@ bool coarse_supported(const mol_shape_t& s) {
   Dims D = dims_of(s);
   if (D.Pq != kPQ || D.H != kH) return false;
   if (D.Px == 8 && D.d == 32) return true;
+  if (D.Px == 4 && (D.d == 64 || D.d == 128)) return true;
   return false;
 }
 
+static size_t qrec_bytes(const Dims& D) { return (size_t)16 * (16 / D.Pq) * D.d * 2 + (size_t)D.L * 2; }
+
 void coarse_plan(const mol_shape_t& s, int chunk, Arena& a, CoarseWs* ws) {
   Dims D = dims_of(s);
-  const int K1 = (16 / D.Pq) * D.d;
-  ws->w1_bf16 = reinterpret_cast<__nv_bfloat16*>(a.take<uint8_t>((size_t)kH * D.L * 2));
-  ws->w2_bf16 = reinterpret_cast<__nv_bfloat16*>(a.take<uint8_t>((size_t)kH * D.L * 2));
-  ws->b1h = a.take<float>(kH);
-  ws->b2h = a.take<float>(D.L);
-  ws->q_bf16 = reinterpret_cast<__nv_bfloat16*>(a.take<uint8_t>((size_t)chunk * 16 * K1 * 2));
-  ws->gqh = a.take<float>((size_t)chunk * D.L);
+  ws->w1_img = a.take<uint8_t>((size_t)kH * (D.L + 16) * 2);
+  ws->w2_img = a.take<uint8_t>((size_t)D.L * kK3 * 2);
+  ws->q_rec = a.take<uint8_t>((size_t)chunk * qrec_bytes(D));
+  ws->overflow = a.take<int32_t>(1);
 }
 
 int coarse_prepare(const mol_shape_t& s, const mol_weights_t& w, const CoarseWs& ws, cudaStream_t st) {
   Dims D = dims_of(s);
-  const int n = kH * D.L;
-  coarse_weight_images_kernel<<<(n + 255) / 256, 256, 0, st>>>(
-      w.qi_w1, w.qi_b1, w.qi_w2, w.qi_b2, reinterpret_cast<uint8_t*>(ws.w1_bf16),
-      reinterpret_cast<uint8_t*>(ws.w2_bf16), ws.b1h, ws.b2h, D.Pq, D.Px);
+  MOL_CUDA(cudaMemsetAsync(ws.overflow, 0, sizeof(int32_t), st));
+  const int n = kH * (D.L + 16) > D.L * kK3 ? kH * (D.L + 16) : D.L * kK3;
+  coarse_weight_images_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.qi_w1, w.qi_b1, w.qi_w2, w.qi_b2, ws.w1_img,
+                                                               ws.w2_img, ws.overflow, D.Pq, D.Px);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
 }
@@ -484,7 +609,7 @@ static int encode_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t r
   cuuint64_t gstride[1] = {cols * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -496,26 +621,28 @@ static int encode_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t r
 
 template <int PX, int DD>
 static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, const float* qsub,
-                         const float* gq, int bc, float* scores, cudaStream_t st) {
+                         const float* gq, int bc, const CoarseOut& out, cudaStream_t st) {
   using C = CoarseCfg<PX, DD>;
   Dims D = dims_of(s);
   const int64_t N = ix.num_items;
   const int64_t Np = (N + kTile - 1) / kTile * kTile;
-  coarse_query_images_kernel<<<bc, 128, 0, st>>>(qsub, gq, reinterpret_cast<uint8_t*>(ws.q_bf16), ws.gqh, bc, D.Pq,
-                                                 D.Px, D.d, 1.0f / s.temperature);
+  coarse_query_records_kernel<<<bc, 128, 0, st>>>(qsub, gq, ws.q_rec, ws.overflow, bc, D.Pq, D.Px, D.d,
+                                                  1.0f / s.temperature);
   MOL_LAUNCH_CHECK();
   CUtensorMap tmX, tmGI;
-  MOL_TRY(encode_2d(&tmX, ix.xsub_bf16, C::XCOLS, (uint64_t)Np, 64, kTile, CU_TENSOR_MAP_SWIZZLE_128B));
-  MOL_TRY(encode_2d(&tmGI, ix.gi_bf16, C::L, (uint64_t)Np, C::L, kTile,
+  MOL_TRY(encode_2d(&tmX, ix.xsub_half, C::XCOLS, (uint64_t)Np, 64, kTile, CU_TENSOR_MAP_SWIZZLE_128B));
+  MOL_TRY(encode_2d(&tmGI, ix.gi_half, C::L, (uint64_t)Np, C::L, kTile,
                     C::L == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
   CoarseParams P;
-  P.w1_img = reinterpret_cast<const uint8_t*>(ws.w1_bf16);
-  P.w2_img = reinterpret_cast<const uint8_t*>(ws.w2_bf16);
-  P.b1h = ws.b1h;
-  P.b2h = ws.b2h;
-  P.q_img = reinterpret_cast<const uint8_t*>(ws.q_bf16);
-  P.gqh = ws.gqh;
-  P.scores = scores;
+  P.w1_img = ws.w1_img;
+  P.w2_img = ws.w2_img;
+  P.q_rec = ws.q_rec;
+  P.scores = out.scores;
+  P.thr = out.thr;
+  P.cand_cnt = out.cand_cnt;
+  P.cand_scores = out.cand_scores;
+  P.cand_idx = out.cand_idx;
+  P.cand_cap = out.cand_cap;
   P.N = N;
   P.n_tiles = (int)(Np / kTile);
   P.bc = bc;
@@ -532,12 +659,21 @@ static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const Coar
   return MOL_OK;
 }
 
-int coarse_scores(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, const float* qsub,
-                  const float* gq, int bc, float* scores, cudaStream_t st) {
+int coarse_run(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, const float* qsub, const float* gq,
+               int bc, const CoarseOut& out, cudaStream_t st) {
   Dims D = dims_of(s);
   if (bc == 0 || ix.num_items == 0) return MOL_OK;
-  if (D.Px == 8 && D.d == 32) return launch_coarse<8, 32>(s, ix, ws, qsub, gq, bc, scores, st);
+  if (D.Px == 8 && D.d == 32) return launch_coarse<8, 32>(s, ix, ws, qsub, gq, bc, out, st);
+  if (D.Px == 4 && D.d == 64) return launch_coarse<4, 64>(s, ix, ws, qsub, gq, bc, out, st);
+  if (D.Px == 4 && D.d == 128) return launch_coarse<4, 128>(s, ix, ws, qsub, gq, bc, out, st);
   MOL_CHECK_ARG(false, "tensor-core path does not support this shape");
+}
+
+int coarse_scores(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, const float* qsub,
+                  const float* gq, int bc, float* scores, cudaStream_t st) {
+  CoarseOut out{};
+  out.scores = scores;
+  return coarse_run(s, ix, ws, qsub, gq, bc, out, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -545,6 +681,7 @@ int coarse_scores(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& w
 // ------------------------------------------------------------------------------------------------
 __global__ void safety_flags_kernel(const float* __restrict__ cand, const float* __restrict__ exact,
                                     const float* __restrict__ topk, int bc, int kk, int k,
+                                    const int32_t* __restrict__ ovf_a, const int32_t* __restrict__ ovf_b,
                                     int32_t* __restrict__ flags) {
   int b = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
   int lane = threadIdx.x % 32;
@@ -556,25 +693,29 @@ __global__ void safety_flags_kernel(const float* __restrict__ cand, const float*
       err = fmaxf(err, fabsf(c - e));
       cmin = fminf(cmin, c);
     }
+    if (c != c) err = CUDART_NAN_F;  // fmaxf would drop a NaN candidate score
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
+    const float e2 = __shfl_xor_sync(0xffffffffu, err, o);
+    err = (err != err || e2 != e2) ? CUDART_NAN_F : fmaxf(err, e2);
     cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
   }
   if (lane == 0) {
     float sk = topk[(int64_t)b * k + (k - 1)];
+    const bool overflow = (ovf_a && *ovf_a) || (ovf_b && *ovf_b);
     // NaN-safe: anything but a provable "no" flags the query for the exact fallback
-    flags[b] = (cmin + 1.5f * err + 1e-3f < sk) ? 0 : 1;
+    flags[b] = (!overflow && cmin + 1.5f * err + 1e-3f < sk) ? 0 : 1;
   }
 }
 
 int coarse_safety_flags(const float* cand_scores, const float* exact_scores, const float* topk_scores,
-                        int bc, int kk, int k, int32_t* flags, cudaStream_t st) {
+                        int bc, int kk, int k, const int32_t* overflow_a, const int32_t* overflow_b,
+                        int32_t* flags, cudaStream_t st) {
   if (bc == 0) return MOL_OK;
   int threads = bc * 32;
-  safety_flags_kernel<<<(threads + 255) / 256, 256, 0, st>>>(cand_scores, exact_scores, topk_scores,
-                                                             bc, kk, k, flags);
+  safety_flags_kernel<<<(threads + 255) / 256, 256, 0, st>>>(cand_scores, exact_scores, topk_scores, bc, kk, k,
+                                                             overflow_a, overflow_b, flags);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
 }

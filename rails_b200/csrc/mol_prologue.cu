@@ -124,7 +124,7 @@ int launch_glu(const float* pre, float* h, int64_t B, int Hq, int kind, cudaStre
 // ------------------------------------------------------------------------------------------
 // One warp per d-vector.
 __global__ void l2norm_groups_kernel(const float* __restrict__ in, float* __restrict__ out_f32,
-                                     __nv_bfloat16* __restrict__ out_bf16, int64_t n_vec, int d,
+                                     __half* __restrict__ out_half, int64_t n_vec, int d,
                                      float eps) {
   int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   int lane = threadIdx.x % 32;
@@ -138,16 +138,16 @@ __global__ void l2norm_groups_kernel(const float* __restrict__ in, float* __rest
   for (int i = lane; i < d; i += 32) {
     float y = p[i] / nrm;
     if (out_f32) out_f32[v * d + i] = y;
-    if (out_bf16) out_bf16[v * d + i] = __float2bfloat16_rn(y);
+    if (out_half) out_half[v * d + i] = __float2half_rn(y);  // |y| <= 1: always representable
   }
 }
 
-int launch_l2norm_groups(const float* in, float* out_f32, __nv_bfloat16* out_bf16, int64_t rows,
+int launch_l2norm_groups(const float* in, float* out_f32, __half* out_half, int64_t rows,
                          int groups, int d, float eps, cudaStream_t st) {
   int64_t n_vec = rows * groups;
   if (n_vec == 0) return MOL_OK;
   int64_t threads = n_vec * 32;
-  l2norm_groups_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, out_f32, out_bf16,
+  l2norm_groups_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, out_f32, out_half,
                                                                           n_vec, d, eps);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
@@ -199,19 +199,6 @@ int launch_query_assemble(const mol_shape_t& s, const mol_weights_t& w, const fl
   int threads = B * D.Pq * 32;
   query_assemble_kernel<<<(threads + 255) / 256, 256, 0, st>>>(proj, user_ids, t, qsub, B, D.Pq,
                                                                D.Pq_proj, D.d, s.eps);
-  MOL_LAUNCH_CHECK();
-  return MOL_OK;
-}
-
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                   int64_t n) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
-}
-
-int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t st) {
-  if (n == 0) return MOL_OK;
-  f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
 }

@@ -206,6 +206,97 @@ __global__ void probe_mufu_kernel(int which, int iters, float seed, float* sink,
   if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Probe 4: issue/pipe throughput of the packed and mixed instruction streams the v2 epilogue relies on.
+// 8 independent chains per thread.  which: 0 ffma (f32), 1 ffma2 (fma.rn.f32x2), 2 hfma2 (f16x2),
+// 3 cvt.rn.f16x2.f32, 4 min.xorsign.abs.f16x2, 5 tanh.approx.f16x2, 6 mix {1 tanh.f32 + 6 ffma},
+// 7 mix {1 ex2.f32 + 3 ffma2}, 8 mix {1 tanh.f16x2 + 4 hfma2}, 9 fadd2.  ops counted = instructions.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hfma2_f16(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t tanh_f16x2_p(uint32_t a) {
+  uint32_t d;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ uint32_t clamp_f16x2_p(uint32_t a, uint32_t c) {
+  uint32_t d;
+  asm("min.xorsign.abs.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_f16x2_p(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__global__ void probe_pipe_kernel(int which, int iters, float seed, float* sink, long long* cycles) {
+  float a[8];
+  float2 f[8];
+  uint32_t u[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = seed + threadIdx.x * 1e-3f + 0.01f * j;
+    f[j] = make_float2(a[j], a[j] + 0.5f);
+    u[j] = pack_f16x2_p(a[j], a[j] * 0.5f);
+  }
+  const float2 m2 = make_float2(0.999f, 1.0001f), c2 = make_float2(0.25f, 0.125f);
+  const uint32_t hm = pack_f16x2_p(0.999f, 0.998f), hc = pack_f16x2_p(0.01f, 0.02f), h3 = pack_f16x2_p(3.f, 3.f);
+  __syncthreads();
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    if (which == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], 0.999f, 0.25f);
+    } else if (which == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __ffma2_rn(f[j], m2, c2);
+    } else if (which == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = hfma2_f16(u[j], hm, hc);
+    } else if (which == 3) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = pack_f16x2_p(__uint_as_float(u[j]), a[j]);
+    } else if (which == 4) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = clamp_f16x2_p(u[j], h3);
+    } else if (which == 5) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = tanh_f16x2_p(u[j]);
+    } else if (which == 6) {
+      a[0] = tanh_approx(a[0]);
+      a[1] = fmaf(a[1], 0.999f, 0.25f); a[2] = fmaf(a[2], 0.999f, 0.25f); a[3] = fmaf(a[3], 0.999f, 0.25f);
+      a[4] = fmaf(a[4], 0.999f, 0.25f); a[5] = fmaf(a[5], 0.999f, 0.25f); a[6] = fmaf(a[6], 0.999f, 0.25f);
+      a[7] = tanh_approx(a[7]);
+      a[1] = fmaf(a[1], 0.999f, 0.25f); a[2] = fmaf(a[2], 0.999f, 0.25f); a[3] = fmaf(a[3], 0.999f, 0.25f);
+      a[4] = fmaf(a[4], 0.999f, 0.25f); a[5] = fmaf(a[5], 0.999f, 0.25f); a[6] = fmaf(a[6], 0.999f, 0.25f);
+    } else if (which == 7) {
+      a[0] = ex2_approx(a[0]);
+      f[1] = __ffma2_rn(f[1], m2, c2); f[2] = __ffma2_rn(f[2], m2, c2); f[3] = __ffma2_rn(f[3], m2, c2);
+      a[7] = ex2_approx(a[7]);
+      f[4] = __ffma2_rn(f[4], m2, c2); f[5] = __ffma2_rn(f[5], m2, c2); f[6] = __ffma2_rn(f[6], m2, c2);
+    } else if (which == 8) {
+      u[0] = tanh_f16x2_p(u[0]);
+      u[1] = hfma2_f16(u[1], hm, hc); u[2] = hfma2_f16(u[2], hm, hc); u[3] = hfma2_f16(u[3], hm, hc); u[4] = hfma2_f16(u[4], hm, hc);
+      u[7] = tanh_f16x2_p(u[7]);
+      u[5] = hfma2_f16(u[5], hm, hc); u[6] = hfma2_f16(u[6], hm, hc); u[1] = hfma2_f16(u[1], hm, hc); u[2] = hfma2_f16(u[2], hm, hc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __fadd2_rn(f[j], c2);
+    }
+  }
+  long long t1 = clock64();
+  __syncthreads();
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc += a[j] + f[j].x + f[j].y + __uint_as_float(u[j]);
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -271,6 +362,17 @@ int probe_mufu(int which, int iters, int threads, int blocks, float* sink, long 
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     fprintf(stderr, "probe_mufu: %s\n", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+// instructions per iteration per thread: 8 (which 0-5, 9), 14 (6), 8 (7), 10 (8)
+int probe_pipe(int which, int iters, int threads, int blocks, float* sink, long long* cycles) {
+  probe_pipe_kernel<<<blocks, threads>>>(which, iters, 0.25f, sink, cycles);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "probe_pipe: %s\n", cudaGetErrorString(e));
     return 1;
   }
   return 0;

@@ -1,9 +1,10 @@
 """CPU model of the NUMERICS of the tcgen05 coarse pass (TEST INFRASTRUCTURE, not product code).
 
 Mirrors rails_b200/csrc/mol_coarse_sm100.cu rounding points with torch ops:
-  * X_sub, Q_sub/tau, GI, 0.5*W1, 0.5*W2 rounded to bf16 (tensor-core operands / smem images),
-  * logits accumulated in fp32, re-rounded to bf16 as the A operand of the hidden GEMM,
-  * hidden activations u + u*tanh(u) (u = 0.5*x) rounded to bf16 as the A operand of the gate GEMM,
+  * X_sub, Q_sub/tau, GI, 0.5*gq, 0.5*W1, 0.5*b1, 0.5*W2, 0.5*b2 rounded to fp16 (tensor-core operands / smem images;
+    the biases ride in a "ones" K-block of the GEMMs, gq*gi is a GEMM against diag(0.5 gq)),
+  * logits accumulated in fp32, re-rounded to fp16 as the A operand of the hidden GEMM,
+  * hidden activations in packed half2: u -> fp16, tanh -> fp16, h = fma(u, tanh u, u) -> fp16 (A operand of the gate GEMM),
   * gate / softmax / weighted sum in fp32 using the fp32 logits.
 Used to validate the candidate-set policy (K') on CPU before spending GPU time, and by GPU tests to
 bound the coarse-vs-exact error the kernel is expected to show.
@@ -13,11 +14,11 @@ import torch
 from oracle import mol_oracle as O
 
 
-def _bf(x):
-    return x.to(torch.bfloat16).to(torch.float32)
+def _h(x):
+    return x.to(torch.float16).to(torch.float32)
 
 
-def coarse_scores(cfg, sd, queries, items, user_ids=None, split_q=False):
+def coarse_scores(cfg, sd, queries, items, user_ids=None):
     sd = {k: v.float() for k, v in sd.items()}
     q = queries.float()
     qs = O.query_sub_embeddings(cfg, sd, q, user_ids)          # (B, Pq, d) fp32 (exact prologue)
@@ -25,18 +26,16 @@ def coarse_scores(cfg, sd, queries, items, user_ids=None, split_q=False):
     gq = O._mlp_silu(q, sd[O.K_GQ_W1], sd[O.K_GQ_B1], sd[O.K_GQ_W2])          # (B, L)
     gi = O._mlp_silu(items.float(), sd[O.K_GI_W1], sd[O.K_GI_B1], sd[O.K_GI_W2])  # (N, L)
     B, N, L = q.size(0), items.size(0), cfg.num_logits
-    qt = qs / cfg.temperature
-    if split_q:
-        qh = _bf(qt)
-        ql = _bf(qt - qh)
-        logits = torch.einsum("bnd,xmd->bxnm", qh, _bf(xs)) + torch.einsum("bnd,xmd->bxnm", ql, _bf(xs))
-    else:
-        logits = torch.einsum("bnd,xmd->bxnm", _bf(qt), _bf(xs))
-    logits = logits.reshape(B, N, L)
-    w1h, w2h = _bf(0.5 * sd[O.K_QI_W1]), _bf(0.5 * sd[O.K_QI_W2])
-    u = torch.nn.functional.linear(_bf(logits), w1h) + 0.5 * sd[O.K_QI_B1]
-    h = _bf(u + u * torch.tanh(u))
-    ug = torch.nn.functional.linear(h, w2h) + (0.5 * gq).unsqueeze(1) * _bf(gi).unsqueeze(0) + 0.5 * sd[O.K_QI_B2]
+    logits = torch.einsum("bnd,xmd->bxnm", _h(qs / cfg.temperature), _h(xs)).reshape(B, N, L)
+    w1h, w2h = _h(0.5 * sd[O.K_QI_W1]), _h(0.5 * sd[O.K_QI_W2])
+    u = _h(torch.nn.functional.linear(_h(logits), w1h) + _h(0.5 * sd[O.K_QI_B1]))
+    t = _h(torch.tanh(u))
+    h = _h(u + u * t)
+    ug = (
+        torch.nn.functional.linear(h, w2h)
+        + _h(0.5 * gq).unsqueeze(1) * _h(gi).unsqueeze(0)
+        + _h(0.5 * sd[O.K_QI_B2])
+    )
     w = ug + ug * torch.tanh(ug)
     p = torch.softmax(w, dim=-1)
     return (p * logits).sum(-1)

@@ -43,7 +43,7 @@ def test_constants_match_header():
 def test_struct_layouts():
     assert ctypes.sizeof(_lib.MolShape) == 4 * (11 + 4 + 1) + 8
     assert ctypes.sizeof(_lib.MolWeights) == 8 * (16 + 4)
-    assert ctypes.sizeof(_lib.MolIndex) == 8 * 7
+    assert ctypes.sizeof(_lib.MolIndex) == 8 * 8
 
 
 @pytest.mark.parametrize("name", golden_names())

@@ -75,11 +75,29 @@ def mufu():
                               "thread_ops_per_clk_per_sm": ops / c}))
 
 
+def pipe():
+    names = [("ffma", 8), ("ffma2", 8), ("hfma2.f16x2", 8), ("cvt.f16x2", 8), ("min.xorsign.abs.f16x2", 8),
+             ("tanh.f16x2", 8), ("mix 2 tanh.f32 + 12 ffma", 14), ("mix 2 ex2.f32 + 6 ffma2", 8),
+             ("mix 2 tanh.f16x2 + 8 hfma2", 10), ("fadd2", 8)]
+    sink = torch.empty(148 * 8 * 1024, device="cuda")
+    cyc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    iters = 4096
+    for which, (name, per_iter) in enumerate(names):
+        for threads in (256, 512):
+            lib.probe_pipe(which, 64, threads, 148, ptr(sink), ptr(cyc))  # warm
+            rc = lib.probe_pipe(which, iters, threads, 148, ptr(sink), ptr(cyc))
+            c = cyc.item()
+            print(json.dumps({"probe": "pipe", "op": name, "threads_per_sm": threads, "rc": rc, "cycles": c,
+                              "thread_instr_per_clk_per_sm": iters * per_iter * threads / c}))
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     if what == "mma":
         mma(int(sys.argv[2]))
     elif what == "tma":
         tma()
+    elif what == "pipe":
+        pipe()
     else:
         mufu()
