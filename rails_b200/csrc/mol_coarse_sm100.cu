@@ -8,7 +8,7 @@
 // (B, N, H) hidden activations and (B, N, L) gates never leave the SM.  Its output only RANKS
 // candidates; final scores come from the fp32 rescoring pass (mol_exact.cu).
 //
-// Mapping (one persistent CTA per SM, 352 threads):
+// Mapping (one persistent CTA per SM, 384 threads; setmaxnreg gives the epilogue warpgroups 208 registers):
 //   warps 0-3   epilogue warpgroup 0  (TMEM slot 0, even queries of the tile's query range)
 //   warps 4-7   epilogue warpgroup 1  (TMEM slot 1, odd queries)
 //   warp 8/9    MMA issuer of slot 0 / slot 1: one thread, blocking mbarrier waits in the slot's fixed order
@@ -43,7 +43,8 @@ constexpr int kPQ = 8;          // query groups supported by this kernel
 constexpr int kH = 128;         // gating hidden width
 constexpr int kTile = 128;      // items per tile (= TMEM lanes)
 constexpr int kEpiThreads = 256;
-constexpr int kThreads = kEpiThreads + 3 * 32;
+constexpr int kThreads = kEpiThreads + 4 * 32;  // + one control warpgroup (issuers, producer, one idle warp)
+constexpr int kEpiRegs = 208, kCtlRegs = 88;  // setmaxnreg split of the register file
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kK3 = kH + 16;    // K of the gate GEMM's TS part: hidden units + the ones block
 constexpr int kSmemLimit = 232448;
@@ -101,7 +102,7 @@ __host__ __device__ inline uint32_t nosw_off(int r, int k, int K) {
 
 struct Bars {
   uint64_t full[2], empty[2];
-  uint64_t q0_ready[2], e1_done[2], e2_done[2];
+  uint64_t q0_ready[2], e1_done[2], e2a_done[2], e2_done[2];
   uint64_t log_full[2], hid_full[2], gate_full[2];
   uint32_t tmem_base;
 };
@@ -111,15 +112,23 @@ struct TileWalk {
   int64_t f, f1;
   int bc;
   int tile, qa, qb;
-  __device__ TileWalk(int64_t f0_, int64_t f1_, int bc_) : f(f0_), f1(f1_), bc(bc_), tile(0), qa(0), qb(0) {}
+  bool started;
+  __device__ TileWalk(int64_t f0_, int64_t f1_, int bc_)
+      : f(f0_), f1(f1_), bc(bc_), tile(0), qa(0), qb(0), started(false) {}
   __device__ bool next() {
     if (f >= f1) return false;
-    tile = (int)(f / bc);
-    qa = (int)(f - (int64_t)tile * bc);
-    int64_t end = (int64_t)(tile + 1) * bc;
-    if (end > f1) end = f1;
-    qb = (int)(end - (int64_t)tile * bc);
-    f = end;
+    if (!started) {  // the only division: later tiles start at query 0 of tile + 1
+      tile = (int)(f / bc);
+      qa = (int)(f - (int64_t)tile * bc);
+      started = true;
+    } else {
+      ++tile;
+      qa = 0;
+    }
+    const int64_t rest = f1 - f;
+    const int room = bc - qa;
+    qb = rest < (int64_t)room ? qa + (int)rest : bc;
+    f += qb - qa;
     return true;
   }
   // queries of slot `wg` in the current tile: qa + wg, qa + wg + 2, ...
@@ -177,6 +186,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_init(&bars->empty[s], 2);
       mbar_init(&bars->q0_ready[s], 128);
       mbar_init(&bars->e1_done[s], 128);
+      mbar_init(&bars->e2a_done[s], 128);
       mbar_init(&bars->e2_done[s], 128);
       mbar_init(&bars->log_full[s], 1);
       mbar_init(&bars->hid_full[s], 1);
@@ -194,11 +204,11 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-
   // this CTA's flat range of (tile, query) units
   const int64_t F = (int64_t)P.n_tiles * P.bc;
   const int64_t f0 = F * blockIdx.x / gridDim.x, f1 = F * (blockIdx.x + 1) / gridDim.x;
 
+  if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
   if (warp == 10) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
@@ -216,7 +226,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ++it;
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp == 8 || warp == 9) {
     // =============================== MMA issuer of slot `wg` ===============================
     if (lane == 0) {
       const int wg = warp - 8;
@@ -229,7 +239,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       uint32_t c1 = 0, c2 = 0;  // completed e1_done / e2_done phases of this slot
       bool first = true, pre_g1 = false;
 
-      auto issue_g1 = [&](int s) {
+      auto issue_g1 = [&](int s) __attribute__((always_inline)) {
         const uint32_t sXa = smem_u32(sX + s * C::X_BYTES);
 #pragma unroll
         for (int g = 0; g < C::NG; ++g) {
@@ -289,9 +299,9 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               issue_g1(sn);
               pre_g1 = true;
             }
-            // ---- G3 once E2 has written A3
-            mbar_wait_sleep(&bars->e2_done[wg], c2 & 1u);
-            ++c2;
+            // ---- G3, first part, once E2 has written the first half of A3 (and staged nothing new: the diag
+            //      was staged by E3 of the previous query, whose reads of GATE are complete by now)
+            mbar_wait_sleep(&bars->e2a_done[wg], c2 & 1u);
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < L / 16; ++ks) {  // GATE = GI_tile . diag(0.5 gq)
@@ -301,7 +311,16 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               umma_ss(base + kColGate, da, db, idesc3, ks > 0);
             }
 #pragma unroll
-            for (int ks = 0; ks < kK3 / 16; ++ks) {  // += [A3 | 1] . [0.5 W2 | 0.5 b2]^T
+            for (int ks = 0; ks < 4; ++ks) {  // += A3[:, 0:64] . (0.5 W2[:, 0:64])^T
+              const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
+              umma_ts(base + kColGate, base + kColHid + ks * 8, db, idesc3, 1u);
+            }
+            // ---- G3, second part, once E2 has written all of A3
+            mbar_wait_sleep(&bars->e2_done[wg], c2 & 1u);
+            ++c2;
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 4; ks < kK3 / 16; ++ks) {  // += [A3[:, 64:128] | 1] . [0.5 W2[:, 64:128] | 0.5 b2]^T
               const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
               umma_ts(base + kColGate, base + kColHid + ks * 8, db, idesc3, 1u);
             }
@@ -314,8 +333,9 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ++it;
       }
     }
-  } else {
+  } else if (warp < 8) {
     // =============================== epilogue warpgroups ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     const int wg = warp >> 2;                 // slot
     const int r = tid & 127;                  // item row within the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -327,15 +347,15 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // prefetched query data: image of the NEXT query to stage, 0.5*gq[r] of the query whose diag is staged next
     uint4 qv[C::QV];
     __half gqv = __float2half(0.f);
-    auto load_image = [&](int q) {
+    auto load_image = [&](int q) __attribute__((always_inline)) {
       const uint4* src = reinterpret_cast<const uint4*>(P.q_rec + (size_t)q * C::QREC_BYTES);
 #pragma unroll
       for (int i = 0; i < C::QV; ++i) qv[i] = __ldg(src + r + i * 128);
     };
-    auto load_gq = [&](int q) {
+    auto load_gq = [&](int q) __attribute__((always_inline)) {
       if (r < L) gqv = reinterpret_cast<const __half*>(P.q_rec + (size_t)q * C::QREC_BYTES + C::Q_BYTES)[r];
     };
-    auto store_image = [&]() {
+    auto store_image = [&]() __attribute__((always_inline)) {
 #pragma unroll
       for (int i = 0; i < C::QV; ++i) reinterpret_cast<uint4*>(sQw)[r + i * 128] = qv[i];
     };
@@ -359,125 +379,165 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int i = 1; i < 8; ++i) ones[i] = 0u;
     const float2 l2e2 = make_float2(kLog2e, kLog2e);
 
-    while (have) {
-      const uint32_t par = cnt & 1u;
-      // ---------------- E1: logits -> registers, fp16 copy -> A2; stage next query image + this query's diag
-      mbar_wait_sleep(&bars->log_full[wg], par);
+    // Stage order per slot: E1(j) -> E3(j-1) -> E2(j).  G2(j) runs on the tensor pipe behind E3(j-1) and
+    // G1(j+1) / G3(j) behind E2(j) / E1(j+1), so the warpgroup rarely waits for an MMA.  The logits of two
+    // queries are live at once, as packed fp16 pairs (pkA / pkB alternate).
+    auto e1 = [&](uint32_t (&pk)[L / 2], bool stage_diag) __attribute__((always_inline)) {
+      mbar_wait_sleep(&bars->log_full[wg], cnt & 1u);
       tc_fence_after();
-      uint32_t lg[L];
-#pragma unroll
-      for (int c = 0; c < L; c += 32) tmem_ld_x32(base + kColLog + c, lg + c);
-      // G1 of this query is complete: its image buffer is free; G3 of the previous query completed before the
-      // previous E3: the diag buffer is free.
-      if (have_n) store_image();
-      if (r < L) *sDw = gqv;
-      fence_proxy_async_smem();
-      tmem_ld_wait_bind32(lg);
-      if constexpr (L == 64) tmem_ld_wait_bind32(lg + 32);
       {
-        uint32_t pk[L / 2];
+        uint32_t la[32], lb[32];
+        tmem_ld_x32(base + kColLog, la);
+        if constexpr (L == 64) tmem_ld_x32(base + kColLog + 32, lb);
+        // G1 of this query is complete: its image buffer is free for the next query
+        if (have_n) store_image();
+        if (stage_diag && r < L) *sDw = gqv;  // first query only: no earlier G3 can be reading the diag buffer
+        fence_proxy_async_smem();
+        tmem_ld_wait_bind32(la);
 #pragma unroll
-        for (int j2 = 0; j2 < L / 2; ++j2)
-          pk[j2] = pack_f16x2(__uint_as_float(lg[2 * j2]), __uint_as_float(lg[2 * j2 + 1]));
+        for (int j2 = 0; j2 < 16; ++j2)
+          pk[j2] = pack_f16x2(__uint_as_float(la[2 * j2]), __uint_as_float(la[2 * j2 + 1]));
         if constexpr (L == 64) {
-          tmem_st_x32(base + kColLog, pk);
-        } else {
-          tmem_st_x16(base + kColLog, pk);
+          tmem_ld_wait_bind32(lb);
+#pragma unroll
+          for (int j2 = 0; j2 < 16; ++j2)
+            pk[16 + j2] = pack_f16x2(__uint_as_float(lb[2 * j2]), __uint_as_float(lb[2 * j2 + 1]));
         }
-        tmem_st_x8(base + kColLog + L / 2, ones);
       }
+      if constexpr (L == 64) {
+        tmem_st_x32(base + kColLog, pk);
+      } else {
+        tmem_st_x16(base + kColLog, pk);
+      }
+      tmem_st_x8(base + kColLog + L / 2, ones);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bars->e1_done[wg]);
-      // prefetch: gq of the next query, image of the one after
-      int tile_nn = 0, q_nn = 0;
-      const bool have_nn = have_n && seq.next(tile_nn, q_nn);
-      if (have_n) load_gq(q_n);
-      if (have_nn) load_image(q_nn);
+    };
 
-      // ---------------- E2: hidden activations (packed half2) -> A3 (in place, first half of HID) + ones block
-      mbar_wait_sleep(&bars->hid_full[wg], par);
+    auto e2 = [&]() __attribute__((always_inline)) {
+      mbar_wait_sleep(&bars->hid_full[wg], cnt & 1u);
       tc_fence_after();
-      {
-        uint32_t va[32], vb[32];
-        auto act = [&](const uint32_t* v, uint32_t col) {
-          uint32_t pk[16];
+      uint32_t va[32], vb[32];
+      auto act = [&](const uint32_t* v, uint32_t col) __attribute__((always_inline)) {
+        uint32_t hk[16];
 #pragma unroll
-          for (int j2 = 0; j2 < 16; ++j2) {
-            const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
-            pk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
-          }
-          tmem_st_x16(base + col, pk);
-        };
-        tmem_ld_x32(base + kColHid, va);
-        tmem_ld_wait_bind32(va);
-        tmem_ld_x32(base + kColHid + 32, vb);
-        act(va, kColHid);
-        tmem_ld_wait_bind32(vb);
-        tmem_ld_x32(base + kColHid + 64, va);
-        act(vb, kColHid + 16);
-        tmem_ld_wait_bind32(va);
-        tmem_ld_x32(base + kColHid + 96, vb);
-        act(va, kColHid + 32);
-        tmem_ld_wait_bind32(vb);
-        act(vb, kColHid + 48);
-        tmem_st_x8(base + kColHid + 64, ones);
-      }
+        for (int j2 = 0; j2 < 16; ++j2) {
+          const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+          hk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
+        }
+        tmem_st_x16(base + col, hk);
+      };
+      tmem_ld_x32(base + kColHid, va);
+      tmem_ld_wait_bind32(va);
+      tmem_ld_x32(base + kColHid + 32, vb);
+      act(va, kColHid);
+      tmem_ld_wait_bind32(vb);
+      tmem_ld_x32(base + kColHid + 64, va);
+      act(vb, kColHid + 16);
+      tmem_st_wait();  // first half of A3 (k < 64) is in TMEM: the issuer may start G3
+      tc_fence_before();
+      mbar_arrive(&bars->e2a_done[wg]);
+      tmem_ld_wait_bind32(va);
+      tmem_ld_x32(base + kColHid + 96, vb);
+      act(va, kColHid + 32);
+      tmem_ld_wait_bind32(vb);
+      act(vb, kColHid + 48);
+      tmem_st_x8(base + kColHid + 64, ones);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bars->e2_done[wg]);
+    };
 
-      // ---------------- E3: gate -> silu -> softmax (no max subtraction) -> weighted sum
-      mbar_wait_sleep(&bars->gate_full[wg], par);
+    // E3 of the query processed one step earlier (barrier phase cnt - 1); also stages the diag of the query whose
+    // E2 follows (its G3 is issued after that E2; the previous G3 is complete once gate_full has fired).
+    auto e3 = [&](const uint32_t (&pk)[L / 2], int tile_p, int q_p, bool stage_diag) __attribute__((always_inline)) {
+      mbar_wait_sleep(&bars->gate_full[wg], (cnt - 1u) & 1u);
       tc_fence_after();
       float2 num[4], den[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) num[i] = den[i] = make_float2(0.f, 0.f);
-      {
-        uint32_t va[32], vb[32];
-        auto gate = [&](const uint32_t* v, const uint32_t* lgc) {
+      uint32_t va[32], vb[32];
+      auto gate = [&](const uint32_t* v, const uint32_t* lgc) __attribute__((always_inline)) {
 #pragma unroll
-          for (int j2 = 0; j2 < 16; ++j2) {
-            const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
-            const float2 a = __fmul2_rn(u, l2e2);
-            const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
-            const float2 x = __ffma2_rn(a, t, a);
-            const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-            den[j2 & 3] = __fadd2_rn(den[j2 & 3], e);
-            num[j2 & 3] = __ffma2_rn(e, make_float2(__uint_as_float(lgc[2 * j2]), __uint_as_float(lgc[2 * j2 + 1])),
-                                     num[j2 & 3]);
-          }
-        };
-        tmem_ld_x32(base + kColGate, va);
-        tmem_ld_wait_bind32(va);
-        if constexpr (L == 64) tmem_ld_x32(base + kColGate + 32, vb);
-        gate(va, lg);
-        if constexpr (L == 64) {
-          tmem_ld_wait_bind32(vb);
-          gate(vb, lg + 32);
+        for (int j2 = 0; j2 < 16; ++j2) {
+          const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+          const float2 a = __fmul2_rn(u, l2e2);
+          const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+          const float2 x = __ffma2_rn(a, t, a);
+          const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          den[j2 & 3] = __fadd2_rn(den[j2 & 3], e);
+          num[j2 & 3] = __ffma2_rn(e, __half22float2(*reinterpret_cast<const __half2*>(&lgc[j2])), num[j2 & 3]);
         }
+      };
+      tmem_ld_x32(base + kColGate, va);
+      if (stage_diag) {
+        if (r < L) *sDw = gqv;
+        fence_proxy_async_smem();
+      }
+      tmem_ld_wait_bind32(va);
+      if constexpr (L == 64) tmem_ld_x32(base + kColGate + 32, vb);
+      gate(va, pk);
+      if constexpr (L == 64) {
+        tmem_ld_wait_bind32(vb);
+        gate(vb, pk + 16);
       }
       const float2 n2 = __fadd2_rn(__fadd2_rn(num[0], num[1]), __fadd2_rn(num[2], num[3]));
       const float2 d2 = __fadd2_rn(__fadd2_rn(den[0], den[1]), __fadd2_rn(den[2], den[3]));
       const float score = __fdividef(n2.x + n2.y, d2.x + d2.y);
-      const int64_t item = (int64_t)tile * kTile + r;
+      const int64_t item = (int64_t)tile_p * kTile + r;
       if (item < P.N) {
-        if (P.scores) P.scores[(size_t)q * P.N + item] = score;
-        if (P.thr && !(score < __ldg(P.thr + q))) {  // NaN passes the filter on purpose
-          const int pos = atomicAdd(P.cand_cnt + q, 1);
+        if (P.scores) P.scores[(size_t)q_p * P.N + item] = score;
+        if (P.thr && !(score < __ldg(P.thr + q_p))) {  // NaN passes the filter on purpose
+          const int pos = atomicAdd(P.cand_cnt + q_p, 1);
           if (pos < P.cand_cap) {
-            P.cand_scores[(size_t)q * P.cand_cap + pos] = score;
-            P.cand_idx[(size_t)q * P.cand_cap + pos] = (int32_t)item;
+            P.cand_scores[(size_t)q_p * P.cand_cap + pos] = score;
+            P.cand_idx[(size_t)q_p * P.cand_cap + pos] = (int32_t)item;
           }
         }
       }
+    };
+
+    uint32_t pkA[L / 2], pkB[L / 2];
+    int tile_p = 0, q_p = 0;
+    bool have_p = false;
+    // one step: E1(cur) -> E3(prev) -> E2(cur); then advance the query window
+    auto step = [&](uint32_t (&pk_cur)[L / 2], const uint32_t (&pk_prev)[L / 2]) __attribute__((always_inline)) {
+      e1(pk_cur, !have_p);
+      // prefetch: gq of the next query (its diag is staged one step later), image of the one after
+      int tile_nn = 0, q_nn = 0;
+      const bool have_nn = have_n && seq.next(tile_nn, q_nn);
+      if (have_p) {
+        // gqv currently holds this query's 0.5*gq (loaded one step ago): E3(prev) stages it, then it is reloaded
+        e3(pk_prev, tile_p, q_p, true);
+      }
+      if (have_n) load_gq(q_n);
+      if (have_nn) load_image(q_nn);
+      e2();
       ++cnt;
+      tile_p = tile;
+      q_p = q;
+      have_p = true;
       tile = tile_n;
       q = q_n;
       have = have_n;
       tile_n = tile_nn;
       q_n = q_nn;
       have_n = have_nn;
+    };
+    while (have) {
+      step(pkA, pkB);
+      if (!have) {
+        e3(pkA, tile_p, q_p, false);
+        have_p = false;
+        break;
+      }
+      step(pkB, pkA);
+      if (!have) {
+        e3(pkB, tile_p, q_p, false);
+        have_p = false;
+        break;
+      }
     }
   }
 
