@@ -21,7 +21,8 @@ MOL_MAX_UID_TABLES = 4
 MOL_MAX_K = 8192
 MODE_AUTO, MODE_EXACT, MODE_TENSOR = 0, 1, 2
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmol_b200.so")
+# MOL_B200_LIB selects another build of the same library (tuning variants made by `python -m rails_b200.build --variant`)
+LIB_PATH = os.environ.get("MOL_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmol_b200.so")
 
 # every symbol include/mol_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = (

@@ -92,5 +92,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defs) -> str:
+    """Tuning build: compiles every source with extra -D flags into lib/libmol_b200_<name>.so (select it with
+    MOL_B200_LIB=<path>).  Objects go to build/<name>/ so the default build is untouched."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    odir = os.path.join(OBJ_DIR, name)
+    os.makedirs(odir, exist_ok=True)
+    objs = []
+
+    def one(src):
+        obj = os.path.join(odir, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defs] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(one, SOURCES))
+    target = os.path.join(OUT_DIR, f"libmol_b200_{name}.so")
+    _link(objs, target)
+    return target
+
+
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print("built", build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        build(force="--force" in sys.argv, verbose=True)

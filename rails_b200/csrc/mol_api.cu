@@ -97,6 +97,13 @@ static IndexLayout index_layout(const Dims& D, int64_t N) {
 }
 
 // ---- search workspace ------------------------------------------------------------------------
+// Tensor mode has two candidate-generation strategies:
+//   matrix : the coarse pass writes the (chunk, N) score matrix, a radix select keeps the K' best per query
+//            (small corpora: the matrix is cheap).
+//   filter : a coarse pass over a SAMPLE of the corpus gives each query a score threshold that about
+//            `cand_target` items of the whole corpus exceed; the main coarse pass then appends every
+//            (score, item) above the threshold to a per-query buffer inside the scoring kernel's epilogue, so
+//            no score matrix is written or re-read.  Too many / too few survivors are caught by the safety check.
 struct SearchWs {
   // query prologue
   float *pre, *h, *proj, *hq, *qsub, *gq;
@@ -107,25 +114,35 @@ struct SearchWs {
   float* stage_out_scores;
   int64_t* stage_out_ids;
   // scoring / selection
-  float* scores;        // (Bc, N) coarse or exact scores of one query chunk
-  float* seg_scores;    // (Bc, S, kk)
+  float* scores;        // matrix mode: (chunk, N) coarse or exact scores; filter mode: (chunk, sample) + exact fallback (chunk_fb, N)
+  float* seg_scores;    // (chunk, S, kk)
   int32_t* seg_idx;
-  float* cand_scores;   // (Bc, K') coarse top-K'
+  float* cand_scores;   // (chunk, K') coarse top-K'
   int32_t* cand_idx;
-  float* exact_scores;  // (Bc, K') rescored
-  int32_t* flags;       // (Bc) fallback flags
+  float* exact_scores;  // (chunk, K') rescored
+  int32_t* flags;       // (chunk) fallback flags
+  // filter mode
+  float* samp_top;      // (chunk, m) sorted top-m of the sample; thr[b] = samp_top[b*m + m-1]
+  int32_t* fcnt;        // (chunk) survivors per query
+  float* fscores;       // (chunk, cap)
+  int32_t* fidx;        // (chunk, cap)
   CoarseWs coarse;
   int chunk;            // queries per chunk
+  int chunk_fb;         // queries per exact-fallback sub-chunk
   int Kp;               // K' (tensor mode)
-  int S;                // segments for the (chunk, N) select
+  int S;                // segments for the (chunk, n) select
+  int filter;           // 1 = filter strategy
+  int64_t sample;       // sample items (multiple of 128)
+  int m;                // sample rank that defines the threshold
+  int cap;              // survivor capacity per query
   size_t total;
 };
 
 static int coarse_candidates(int k, int64_t N) {
-  // K' = 8k, at least 1024 (rescoring K' pairs costs ~K'/N of the coarse pass, so be generous: the
-  // wider the margin, the rarer the exact fallback), rounded up to 32, capped by N and MOL_MAX_K.
-  int64_t kp = 8 * (int64_t)k;
-  if (kp < 1024) kp = 1024;
+  // K' = max(2k, k + 156) rounded up to 32 (fp16 operands: the exact top-k sits in the coarse top-(k + k/4) in
+  // every case tried, tests/sim_coarse.py; rescoring K' pairs costs ~K'/N of the coarse pass), capped by N.
+  int64_t kp = 2 * (int64_t)k;
+  if (kp < (int64_t)k + 156) kp = (int64_t)k + 156;
   kp = (kp + 31) / 32 * 32;
   if (kp > MOL_MAX_K) kp = MOL_MAX_K;
   if (kp > N) kp = N;
@@ -137,6 +154,8 @@ static bool use_tensor(const mol_shape_t& s, int mode) {
   if (mode == MOL_MODE_EXACT) return false;
   return coarse_supported(s);
 }
+
+constexpr int64_t kFilterMinItems = 1 << 18;
 
 static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, void* base,
                        size_t cap, SearchWs* ws) {
@@ -155,23 +174,66 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
   ws->stage_uid = a.take<int64_t>((size_t)B);
   ws->stage_out_scores = a.take<float>((size_t)B * k);
   ws->stage_out_ids = a.take<int64_t>((size_t)B * k);
-  // query chunk so that the (chunk, N) score matrix stays <= 4 GiB
-  int64_t max_rows = (int64_t)(4ull << 30) / (sizeof(float) * (size_t)(N > 0 ? N : 1));
-  if (max_rows < 1) max_rows = 1;
-  int chunk = (int)(B < max_rows ? B : max_rows);
-  if (chunk < 1) chunk = 1;
-  ws->chunk = chunk;
   ws->Kp = tensor ? coarse_candidates(k, N) : k;
-  ws->S = select_num_segments(N, chunk, ws->Kp);
-  ws->scores = a.take<float>((size_t)chunk * (size_t)N);
-  ws->seg_scores = a.take<float>((size_t)chunk * ws->S * ws->Kp);
-  ws->seg_idx = a.take<int32_t>((size_t)chunk * ws->S * ws->Kp);
-  ws->cand_scores = a.take<float>((size_t)chunk * ws->Kp);
-  ws->cand_idx = a.take<int32_t>((size_t)chunk * ws->Kp);
-  ws->exact_scores = a.take<float>((size_t)chunk * ws->Kp);
-  ws->flags = a.take<int32_t>((size_t)chunk);
+  // filter strategy: capacity 4 K' (>= 4096), aiming at capacity / 4 survivors
+  ws->cap = 4 * ws->Kp < 4096 ? 4096 : 4 * ws->Kp;
+  ws->filter = (tensor && N >= kFilterMinItems && (int64_t)ws->cap * 16 <= N) ? 1 : 0;
+  const int64_t n_rows = N > 0 ? N : 1;
+  if (ws->filter) {
+    const int64_t target = ws->cap / 4;
+    int64_t sample = 32 * N / target;  // -> threshold rank m >= 32 in the sample
+    if (sample < 32768) sample = 32768;
+    sample = (sample + 127) / 128 * 128;
+    ws->sample = sample;
+    ws->m = (int)((target * sample + N - 1) / N);
+    ws->chunk = B < 1 ? 1 : B;
+    int64_t fb = (int64_t)(1ull << 30) / (int64_t)(sizeof(float) * (size_t)n_rows);
+    if (fb < 1) fb = 1;
+    ws->chunk_fb = (int)(fb < ws->chunk ? fb : ws->chunk);
+    // the (chunk, sample) matrix of the threshold pass; query chunks keep it <= 2 GiB
+    int64_t max_rows = (int64_t)(2ull << 30) / (int64_t)(sizeof(float) * (size_t)sample);
+    if (max_rows < 1) max_rows = 1;
+    if (ws->chunk > max_rows) ws->chunk = (int)max_rows;
+    if (ws->chunk_fb > ws->chunk) ws->chunk_fb = ws->chunk;
+    size_t n_scores = (size_t)ws->chunk * (size_t)sample;
+    if ((size_t)ws->chunk_fb * (size_t)n_rows > n_scores) n_scores = (size_t)ws->chunk_fb * (size_t)n_rows;
+    ws->scores = a.take<float>(n_scores);
+    // segment survivors of any (rows <= chunk, kk <= max(m, k)) select: rows * S(rows) < rows + 2 * 148 + 1
+    const int kk_max = ws->m > k ? ws->m : k;
+    const size_t seg = (size_t)(ws->chunk + 2 * 148 + 1) * kk_max;
+    ws->S = 0;
+    ws->seg_scores = a.take<float>(seg);
+    ws->seg_idx = a.take<int32_t>(seg);
+    ws->samp_top = a.take<float>((size_t)ws->chunk * ws->m);
+    ws->fcnt = a.take<int32_t>((size_t)ws->chunk);
+    ws->fscores = a.take<float>((size_t)ws->chunk * ws->cap);
+    ws->fidx = a.take<int32_t>((size_t)ws->chunk * ws->cap);
+  } else {
+    // query chunk so that the (chunk, N) score matrix stays <= 4 GiB
+    int64_t max_rows = (int64_t)(4ull << 30) / (int64_t)(sizeof(float) * (size_t)n_rows);
+    if (max_rows < 1) max_rows = 1;
+    int chunk = (int)(B < max_rows ? B : max_rows);
+    if (chunk < 1) chunk = 1;
+    ws->chunk = chunk;
+    ws->chunk_fb = chunk;
+    ws->sample = 0;
+    ws->m = 0;
+    ws->S = 0;
+    ws->scores = a.take<float>((size_t)chunk * (size_t)N);
+    const size_t seg = (size_t)(chunk + 2 * 148 + 1) * (ws->Kp > k ? ws->Kp : k);
+    ws->seg_scores = a.take<float>(seg);
+    ws->seg_idx = a.take<int32_t>(seg);
+    ws->samp_top = nullptr;
+    ws->fcnt = nullptr;
+    ws->fscores = nullptr;
+    ws->fidx = nullptr;
+  }
+  ws->cand_scores = a.take<float>((size_t)ws->chunk * ws->Kp);
+  ws->cand_idx = a.take<int32_t>((size_t)ws->chunk * ws->Kp);
+  ws->exact_scores = a.take<float>((size_t)ws->chunk * ws->Kp);
+  ws->flags = a.take<int32_t>((size_t)ws->chunk);
   memset(&ws->coarse, 0, sizeof(ws->coarse));
-  if (tensor) coarse_plan(s, chunk, a, &ws->coarse);
+  if (tensor) coarse_plan(s, ws->chunk, a, &ws->coarse);
   ws->total = align_up(a.off, 256);
   if (base != nullptr && a.off > cap) {
     set_error("workspace too small: need %zu bytes, got %zu", ws->total, cap);
@@ -196,6 +258,43 @@ static int run_query_prologue(const mol_shape_t& s, const mol_weights_t& w, cons
   return MOL_OK;
 }
 
+// top-kk of each row of a (bc, n) device score matrix -> (out_scores, out_idx / out_ids), sorted
+static int topk_of_matrix(const SearchWs& ws, const float* scores, int64_t n, int64_t ld, int bc, int kk,
+                          float* out_scores, int32_t* out_idx, int64_t* out_ids, const int64_t* id_map,
+                          const int32_t* flags, cudaStream_t st) {
+  const int S = select_num_segments(n, bc, kk);
+  const float* sel_scores = scores;
+  const int32_t* sel_payload = nullptr;
+  int64_t sel_n = n, sel_ld = ld;
+  if (S > 1) {
+    MOL_TRY(launch_select_segments(scores, n, ld, bc, S, kk, ws.seg_scores, ws.seg_idx, flags, st));
+    sel_scores = ws.seg_scores;
+    sel_payload = ws.seg_idx;
+    sel_n = (int64_t)S * kk;
+    sel_ld = sel_n;
+  }
+  return launch_select_final_i32(sel_scores, sel_payload, sel_n, sel_ld, bc, kk, out_scores, out_idx, out_ids,
+                                 id_map, flags, st);
+}
+
+// Flagged queries are re-done exactly, in sub-chunks whose (rows, N) fp32 matrix fits the workspace (kernels
+// exit immediately for unflagged rows).
+static int exact_fallback(const mol_shape_t& s, const mol_weights_t& w, const mol_index_t& ix, const SearchWs& ws,
+                          const float* qsub, const float* gq, int bc, int k, float* o_scores, int64_t* o_ids,
+                          cudaStream_t st) {
+  Dims D = dims_of(s);
+  const int64_t N = ix.num_items;
+  for (int b1 = 0; b1 < bc; b1 += ws.chunk_fb) {
+    const int nb = (bc - b1 < ws.chunk_fb) ? (bc - b1) : ws.chunk_fb;
+    const int32_t* fl = ws.flags + b1;
+    MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub + (size_t)b1 * D.Pq * D.d, gq + (size_t)b1 * D.L, nb,
+                                nullptr, N, N, ws.scores, fl, st));
+    MOL_TRY(topk_of_matrix(ws, ws.scores, N, N, nb, k, o_scores + (size_t)b1 * k, nullptr, o_ids + (size_t)b1 * k,
+                           ix.item_ids, fl, st));
+  }
+  return MOL_OK;
+}
+
 static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_index_t& ix,
                        const float* queries, const int64_t* user_ids, int B, int k, int mode,
                        float* out_scores, int64_t* out_ids, const SearchWs& ws, cudaStream_t st) {
@@ -214,58 +313,65 @@ static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_i
     const float* gq = ws.gq + (size_t)b0 * D.L;
     float* o_scores = out_scores + (size_t)b0 * k;
     int64_t* o_ids = out_ids + (size_t)b0 * k;
-    const int kk = tensor ? ws.Kp : k;
-    prof_begin(st);
-    if (tensor) {
-      MOL_TRY(coarse_scores(s, ix, ws.coarse, qsub, gq, bc, ws.scores, st));
-    } else {
-      MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub, gq, bc, nullptr, N, N, ws.scores,
-                                  nullptr, st));
-    }
-    prof_end(st);
-    // top-kk of each row of the (bc, N) score matrix
-    const float* sel_scores = ws.scores;
-    const int32_t* sel_payload = nullptr;
-    int64_t sel_n = N, sel_ld = N;
-    if (ws.S > 1) {
-      MOL_TRY(launch_select_segments(ws.scores, N, N, bc, ws.S, kk, ws.seg_scores, ws.seg_idx,
-                                     nullptr, st));
-      sel_scores = ws.seg_scores;
-      sel_payload = ws.seg_idx;
-      sel_n = (int64_t)ws.S * kk;
-      sel_ld = sel_n;
-    }
     if (!tensor) {
-      MOL_TRY(launch_select_final_i32(sel_scores, sel_payload, sel_n, sel_ld, bc, k, o_scores,
-                                      nullptr, o_ids, ix.item_ids, nullptr, st));
+      prof_begin(st);
+      MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub, gq, bc, nullptr, N, N, ws.scores, nullptr, st));
+      prof_end(st);
+      MOL_TRY(topk_of_matrix(ws, ws.scores, N, N, bc, k, o_scores, nullptr, o_ids, ix.item_ids, nullptr, st));
+      continue;
+    }
+    const int kk = ws.Kp;
+    const float* thr = nullptr;
+    if (!ws.filter) {
+      // matrix strategy: coarse scores of every pair -> top-K' per query
+      prof_begin(st);
+      MOL_TRY(coarse_scores(s, ix, ws.coarse, qsub, gq, bc, ws.scores, st));
+      prof_end(st);
+      MOL_TRY(topk_of_matrix(ws, ws.scores, N, N, bc, kk, ws.cand_scores, ws.cand_idx, nullptr, nullptr, nullptr, st));
     } else {
-      // coarse top-K' -> exact fp32 rescoring -> final top-k (+ safety check and per-query fallback)
-      MOL_TRY(launch_select_final_i32(sel_scores, sel_payload, sel_n, sel_ld, bc, kk,
-                                      ws.cand_scores, ws.cand_idx, nullptr, nullptr, nullptr, st));
-      MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub, gq, bc, ws.cand_idx, kk, kk,
-                                  ws.exact_scores, nullptr, st));
-      MOL_TRY(launch_select_final_i32(ws.exact_scores, ws.cand_idx, kk, kk, bc, k, o_scores,
-                                      nullptr, o_ids, ix.item_ids, nullptr, st));
-      if (kk < N) {
-        MOL_TRY(coarse_safety_flags(ws.cand_scores, ws.exact_scores, o_scores, bc, kk, k, ws.coarse.overflow,
-                                    ix.half_overflow, ws.flags, st));
-        // flagged queries are re-done exactly (kernels exit immediately for unflagged rows)
-        MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub, gq, bc, nullptr, N, N,
-                                    ws.scores, ws.flags, st));
-        const float* f_scores = ws.scores;
-        const int32_t* f_payload = nullptr;
-        int64_t f_n = N, f_ld = N;
-        if (ws.S > 1) {
-          MOL_TRY(launch_select_segments(ws.scores, N, N, bc, ws.S, kk, ws.seg_scores, ws.seg_idx,
-                                         ws.flags, st));
-          f_scores = ws.seg_scores;
-          f_payload = ws.seg_idx;
-          f_n = (int64_t)ws.S * kk;
-          f_ld = f_n;
-        }
-        MOL_TRY(launch_select_final_i32(f_scores, f_payload, f_n, f_ld, bc, k, o_scores, nullptr,
-                                        o_ids, ix.item_ids, ws.flags, st));
-      }
+      // filter strategy.  (1) threshold pass over the first `sample` items
+      const int sample_tiles = (int)(ws.sample / 128);
+      CoarseOut o1{};
+      o1.scores = ws.scores;
+      o1.ld = ws.sample;
+      o1.tile_begin = 0;
+      o1.tile_end = sample_tiles;
+      prof_begin(st);
+      MOL_TRY(coarse_run(s, ix, ws.coarse, qsub, gq, bc, o1, st));
+      prof_end(st);
+      MOL_TRY(topk_of_matrix(ws, ws.scores, ws.sample, ws.sample, bc, ws.m, ws.samp_top, nullptr, nullptr, nullptr,
+                             nullptr, st));
+      thr = ws.samp_top + (ws.m - 1);  // stride m
+      // (2) survivors of the sample, then the main pass with the filter fused into the scoring kernel
+      MOL_CUDA(cudaMemsetAsync(ws.fcnt, 0, (size_t)bc * sizeof(int32_t), st));
+      MOL_CUDA(cudaMemsetAsync(ws.fidx, 0xFF, (size_t)bc * ws.cap * sizeof(int32_t), st));
+      MOL_TRY(coarse_filter_matrix(ws.scores, ws.sample, ws.sample, bc, thr, ws.m, ws.fcnt, ws.fscores, ws.fidx,
+                                   ws.cap, st));
+      CoarseOut o2{};
+      o2.thr = thr;
+      o2.thr_stride = ws.m;
+      o2.cand_cnt = ws.fcnt;
+      o2.cand_scores = ws.fscores;
+      o2.cand_idx = ws.fidx;
+      o2.cand_cap = ws.cap;
+      o2.tile_begin = sample_tiles;
+      o2.tile_end = -1;
+      prof_begin(st);
+      MOL_TRY(coarse_run(s, ix, ws.coarse, qsub, gq, bc, o2, st));
+      prof_end(st);
+      // (3) the K' best survivors per query
+      MOL_TRY(launch_select_final_i32(ws.fscores, ws.fidx, ws.cap, ws.cap, bc, kk, ws.cand_scores, ws.cand_idx,
+                                      nullptr, nullptr, nullptr, st));
+    }
+    // exact fp32 rescoring of the K' candidates -> final top-k (+ safety check and per-query exact fallback)
+    MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub, gq, bc, ws.cand_idx, kk, kk, ws.exact_scores,
+                                nullptr, st));
+    MOL_TRY(launch_select_final_i32(ws.exact_scores, ws.cand_idx, kk, kk, bc, k, o_scores, nullptr, o_ids,
+                                    ix.item_ids, nullptr, st));
+    if (kk < N) {
+      MOL_TRY(coarse_safety_flags(ws.cand_scores, ws.exact_scores, o_scores, bc, kk, k, ws.coarse.overflow,
+                                  ix.half_overflow, ws.filter ? ws.fcnt : nullptr, thr, ws.m, ws.cap, ws.flags, st));
+      MOL_TRY(exact_fallback(s, w, ix, ws, qsub, gq, bc, k, o_scores, o_ids, st));
     }
   }
   return MOL_OK;

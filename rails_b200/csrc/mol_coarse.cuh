@@ -13,8 +13,12 @@ struct CoarseWs {
 
 // Where the coarse pass puts its results (any subset).
 struct CoarseOut {
-  float* scores;       // (bc, N) row stride N, or nullptr
-  const float* thr;    // (bc) per-query thresholds of the fused candidate filter, or nullptr
+  float* scores;       // (bc, ld): column = item - tile_begin * 128; or nullptr
+  int64_t ld;          // row stride of `scores`
+  int tile_begin;      // item tiles (128 items) [tile_begin, tile_end) are scored; tile_end < 0 = to the end
+  int tile_end;
+  const float* thr;    // per-query thresholds of the fused candidate filter: thr[b * thr_stride]; or nullptr
+  int thr_stride;
   int32_t* cand_cnt;   // (bc) counters (zeroed by the caller)
   float* cand_scores;  // (bc, cand_cap)
   int32_t* cand_idx;   // (bc, cand_cap)
@@ -38,8 +42,14 @@ int coarse_gi_image(const mol_shape_t& s, const float* gi_f32, uint16_t* gi_half
 // flags[b] = 1 when the coarse candidate set cannot be shown to contain the exact top-k:
 //   cand_scores[b, kk-1] + 1.5 * max_j |cand_scores[b,j] - exact_scores[b,j]| + 1e-3 >= topk_scores[b, k-1]
 // or when either overflow flag is set (operands did not fit fp16).
+// Filter strategy (cnt != nullptr): a query with fewer than kk survivors uses its threshold as the bound on every
+// item outside the candidate set; more survivors than `cap` (dropped candidates) flag the query.
 int coarse_safety_flags(const float* cand_scores, const float* exact_scores, const float* topk_scores,
                         int bc, int kk, int k, const int32_t* overflow_a, const int32_t* overflow_b,
-                        int32_t* flags, cudaStream_t st);
+                        const int32_t* cnt, const float* thr, int thr_stride, int cap, int32_t* flags,
+                        cudaStream_t st);
+// Appends every (score, column) of a (bc, n) matrix with !(score < thr[b]) to the per-query candidate buffers.
+int coarse_filter_matrix(const float* scores, int64_t n, int64_t ld, int bc, const float* thr, int thr_stride,
+                         int32_t* cnt, float* cand_scores, int32_t* cand_idx, int cap, cudaStream_t st);
 
 }  // namespace mol

@@ -48,6 +48,11 @@ constexpr int kEpiRegs = 208, kCtlRegs = 88;  // setmaxnreg split of the registe
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kK3 = kH + 16;    // K of the gate GEMM's TS part: hidden units + the ones block
 constexpr int kSmemLimit = 232448;
+constexpr float kGateClamp = 40.f;  // clamp of the half gate pre-activation u (silu(2u) <= 80 -> e^w finite in fp32)
+#ifndef MOL_EX2_EMU_OF4
+#define MOL_EX2_EMU_OF4 0  // measured on B200: 0 is fastest ("what did not work")
+#endif
+constexpr int kEx2EmuOf4 = MOL_EX2_EMU_OF4;  // of every 4 logit pairs, how many take 2^x on the FMA pipe instead of MUFU.EX2
 
 // TMEM column map of one slot (256 columns)
 constexpr uint32_t kColLog = 0;     // LOG fp32 [0, L); A2 fp16 aliases [0, L/2) + ones [L/2, L/2 + 8)
@@ -85,13 +90,15 @@ struct CoarseParams {
   const uint8_t* q_rec;   // (bc, QREC_BYTES)
   float* scores;          // (bc, N) or nullptr
   // fused candidate filter (all nullptr when unused)
-  const float* thr;       // (bc) per-query threshold
+  const float* thr;       // per-query threshold thr[q * thr_stride]
+  int thr_stride;
   int32_t* cand_cnt;      // (bc) running counters
   float* cand_scores;     // (bc, cand_cap)
   int32_t* cand_idx;      // (bc, cand_cap)
   int cand_cap;
   int64_t N;
-  int n_tiles;
+  int64_t ld;             // row stride of `scores`
+  int tile_begin, tile_end;  // item tiles [tile_begin, tile_end) are scored; scores column = item - tile_begin * 128
   int bc;
 };
 
@@ -205,8 +212,9 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
   // this CTA's flat range of (tile, query) units
-  const int64_t F = (int64_t)P.n_tiles * P.bc;
+  const int64_t F = (int64_t)(P.tile_end - P.tile_begin) * P.bc;
   const int64_t f0 = F * blockIdx.x / gridDim.x, f1 = F * (blockIdx.x + 1) / gridDim.x;
+  const int t0 = P.tile_begin;
 
   if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
   if (warp == 10) {
@@ -221,8 +229,8 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_arrive_expect_tx(&bars->full[s], C::X_BYTES + C::GI_BYTES);
 #pragma unroll
         for (int bx = 0; bx < C::XBOXES; ++bx)
-          tma_load_2d(sX + s * C::X_BYTES + bx * 16384, &tmX, &bars->full[s], bx * 64, w.tile * kTile);
-        tma_load_2d(sGI + s * C::GI_BYTES, &tmGI, &bars->full[s], 0, w.tile * kTile);
+          tma_load_2d(sX + s * C::X_BYTES + bx * 16384, &tmX, &bars->full[s], bx * 64, (t0 + w.tile) * kTile);
+        tma_load_2d(sGI + s * C::GI_BYTES, &tmGI, &bars->full[s], 0, (t0 + w.tile) * kTile);
         ++it;
       }
     }
@@ -378,6 +386,12 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
     for (int i = 1; i < 8; ++i) ones[i] = 0u;
     const float2 l2e2 = make_float2(kLog2e, kLog2e);
+    const float2 magic2 = make_float2(12582912.f, 12582912.f), nmagic2 = make_float2(-12582912.f, -12582912.f);
+    const float2 neg1 = make_float2(-1.f, -1.f);
+    const float2 ec0 = make_float2(0.9999280571937561f, 0.9999280571937561f);
+    const float2 ec1 = make_float2(0.6932609677314758f, 0.6932609677314758f);
+    const float2 ec2 = make_float2(0.2426111251115799f, 0.2426111251115799f);
+    const float2 ec3 = make_float2(0.0551716685295105f, 0.0551716685295105f);
 
     // Stage order per slot: E1(j) -> E3(j-1) -> E2(j).  G2(j) runs on the tensor pipe behind E3(j-1) and
     // G1(j+1) / G3(j) behind E2(j) / E1(j+1), so the warpgroup rarely waits for an MMA.  The logits of two
@@ -452,6 +466,8 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // E3 of the query processed one step earlier (barrier phase cnt - 1); also stages the diag of the query whose
     // E2 follows (its G3 is issued after that E2; the previous G3 is complete once gate_full has fired).
     auto e3 = [&](const uint32_t (&pk)[L / 2], int tile_p, int q_p, bool stage_diag) __attribute__((always_inline)) {
+      // the filter threshold of this query: loaded now, used after the weighted sum
+      const float thr_q = P.thr ? __ldg(P.thr + (size_t)q_p * P.thr_stride) : -CUDART_INF_F;
       mbar_wait_sleep(&bars->gate_full[wg], (cnt - 1u) & 1u);
       tc_fence_after();
       float2 num[4], den[4];
@@ -461,11 +477,29 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       auto gate = [&](const uint32_t* v, const uint32_t* lgc) __attribute__((always_inline)) {
 #pragma unroll
         for (int j2 = 0; j2 < 16; ++j2) {
-          const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+          float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+          if (kEx2EmuOf4 > 0) {  // the exponent-field trick has no inf: keep e^w finite (w = silu(2u) <= 80)
+            u.x = fminf(u.x, kGateClamp);
+            u.y = fminf(u.y, kGateClamp);
+          }
           const float2 a = __fmul2_rn(u, l2e2);
           const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
-          const float2 x = __ffma2_rn(a, t, a);
-          const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          const float2 x = __ffma2_rn(a, t, a);  // w * log2(e), in [-0.41, 116]
+          float2 e;
+          if ((j2 & 3) < kEx2EmuOf4) {
+            // 2^x on the FMA pipe: x = n + f, n = round(x) through the 1.5*2^23 trick, 2^f by a cubic (7.5e-5 rel.),
+            // 2^n by adding n to the exponent field (low mantissa bits of m hold n)
+            const float2 m = __fadd2_rn(x, magic2);
+            const float2 n = __fadd2_rn(m, nmagic2);
+            const float2 f = __ffma2_rn(n, neg1, x);
+            float2 pl = __ffma2_rn(ec3, f, ec2);
+            pl = __ffma2_rn(pl, f, ec1);
+            pl = __ffma2_rn(pl, f, ec0);
+            e.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(m.x) << 23));
+            e.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(m.y) << 23));
+          } else {
+            e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          }
           den[j2 & 3] = __fadd2_rn(den[j2 & 3], e);
           num[j2 & 3] = __ffma2_rn(e, __half22float2(*reinterpret_cast<const __half2*>(&lgc[j2])), num[j2 & 3]);
         }
@@ -485,10 +519,10 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const float2 n2 = __fadd2_rn(__fadd2_rn(num[0], num[1]), __fadd2_rn(num[2], num[3]));
       const float2 d2 = __fadd2_rn(__fadd2_rn(den[0], den[1]), __fadd2_rn(den[2], den[3]));
       const float score = __fdividef(n2.x + n2.y, d2.x + d2.y);
-      const int64_t item = (int64_t)tile_p * kTile + r;
+      const int64_t item = (int64_t)(t0 + tile_p) * kTile + r;
       if (item < P.N) {
-        if (P.scores) P.scores[(size_t)q_p * P.N + item] = score;
-        if (P.thr && !(score < __ldg(P.thr + q_p))) {  // NaN passes the filter on purpose
+        if (P.scores) P.scores[(size_t)q_p * P.ld + ((int64_t)tile_p * kTile + r)] = score;
+        if (P.thr && !(score < thr_q)) {  // NaN passes the filter on purpose
           const int pos = atomicAdd(P.cand_cnt + q_p, 1);
           if (pos < P.cand_cap) {
             P.cand_scores[(size_t)q_p * P.cand_cap + pos] = score;
@@ -699,19 +733,23 @@ static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const Coar
   P.q_rec = ws.q_rec;
   P.scores = out.scores;
   P.thr = out.thr;
+  P.thr_stride = out.thr_stride;
   P.cand_cnt = out.cand_cnt;
   P.cand_scores = out.cand_scores;
   P.cand_idx = out.cand_idx;
   P.cand_cap = out.cand_cap;
   P.N = N;
-  P.n_tiles = (int)(Np / kTile);
+  P.ld = out.ld;
+  P.tile_begin = out.tile_begin;
+  P.tile_end = out.tile_end < 0 ? (int)(Np / kTile) : out.tile_end;
   P.bc = bc;
+  if (P.tile_end <= P.tile_begin) return MOL_OK;
   auto kern = mol_coarse_kernel<PX, DD>;
   MOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   int dev = 0, sms = 148;
   MOL_CUDA(cudaGetDevice(&dev));
   MOL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t F = (int64_t)P.n_tiles * bc;
+  const int64_t F = (int64_t)(P.tile_end - P.tile_begin) * bc;
   int grid = (int)(F < sms ? F : sms);
   if (grid < 1) grid = 1;
   kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(tmX, tmGI, P);
@@ -733,7 +771,42 @@ int coarse_scores(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& w
                   const float* gq, int bc, float* scores, cudaStream_t st) {
   CoarseOut out{};
   out.scores = scores;
+  out.ld = ix.num_items;
+  out.tile_begin = 0;
+  out.tile_end = -1;
   return coarse_run(s, ix, ws, qsub, gq, bc, out, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Survivors of a score matrix (the sample of the threshold pass).
+// ------------------------------------------------------------------------------------------------
+__global__ void filter_matrix_kernel(const float* __restrict__ scores, int64_t n, int64_t ld, const float* __restrict__ thr,
+                                     int thr_stride, int32_t* __restrict__ cnt, float* __restrict__ cand_scores,
+                                     int32_t* __restrict__ cand_idx, int cap) {
+  const int b = blockIdx.y;
+  const float t = thr[(size_t)b * thr_stride];
+  const float* row = scores + (size_t)b * ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = row[i];
+    if (!(v < t)) {
+      const int pos = atomicAdd(cnt + b, 1);
+      if (pos < cap) {
+        cand_scores[(size_t)b * cap + pos] = v;
+        cand_idx[(size_t)b * cap + pos] = (int32_t)i;
+      }
+    }
+  }
+}
+
+int coarse_filter_matrix(const float* scores, int64_t n, int64_t ld, int bc, const float* thr, int thr_stride,
+                         int32_t* cnt, float* cand_scores, int32_t* cand_idx, int cap, cudaStream_t st) {
+  if (bc == 0 || n == 0) return MOL_OK;
+  int64_t gx = (n + 1023) / 1024;
+  if (gx > 64) gx = 64;
+  dim3 grid((unsigned)gx, (unsigned)bc);
+  filter_matrix_kernel<<<grid, 256, 0, st>>>(scores, n, ld, thr, thr_stride, cnt, cand_scores, cand_idx, cap);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -742,7 +815,8 @@ int coarse_scores(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& w
 __global__ void safety_flags_kernel(const float* __restrict__ cand, const float* __restrict__ exact,
                                     const float* __restrict__ topk, int bc, int kk, int k,
                                     const int32_t* __restrict__ ovf_a, const int32_t* __restrict__ ovf_b,
-                                    int32_t* __restrict__ flags) {
+                                    const int32_t* __restrict__ cnt, const float* __restrict__ thr, int thr_stride,
+                                    int cap, int32_t* __restrict__ flags) {
   int b = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
   int lane = threadIdx.x % 32;
   if (b >= bc) return;
@@ -763,19 +837,26 @@ __global__ void safety_flags_kernel(const float* __restrict__ cand, const float*
   }
   if (lane == 0) {
     float sk = topk[(int64_t)b * k + (k - 1)];
-    const bool overflow = (ovf_a && *ovf_a) || (ovf_b && *ovf_b);
+    bool bad = (ovf_a && *ovf_a) || (ovf_b && *ovf_b);
+    if (cnt) {
+      const int c = cnt[b];
+      if (c > cap) bad = true;                              // survivors were dropped
+      if (c <= kk) cmin = thr[(size_t)b * thr_stride];      // every survivor is a candidate: outsiders are below thr
+    }
     // NaN-safe: anything but a provable "no" flags the query for the exact fallback
-    flags[b] = (!overflow && cmin + 1.5f * err + 1e-3f < sk) ? 0 : 1;
+    flags[b] = (!bad && cmin + 1.5f * err + 1e-3f < sk) ? 0 : 1;
   }
 }
 
 int coarse_safety_flags(const float* cand_scores, const float* exact_scores, const float* topk_scores,
                         int bc, int kk, int k, const int32_t* overflow_a, const int32_t* overflow_b,
-                        int32_t* flags, cudaStream_t st) {
+                        const int32_t* cnt, const float* thr, int thr_stride, int cap, int32_t* flags,
+                        cudaStream_t st) {
   if (bc == 0) return MOL_OK;
   int threads = bc * 32;
   safety_flags_kernel<<<(threads + 255) / 256, 256, 0, st>>>(cand_scores, exact_scores, topk_scores, bc, kk, k,
-                                                             overflow_a, overflow_b, flags);
+                                                             overflow_a, overflow_b, cnt, thr, thr_stride, cap,
+                                                             flags);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
 }

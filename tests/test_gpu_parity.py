@@ -207,6 +207,26 @@ def test_full_size_properties_1m_items():
     assert r["max_score_err"] <= SCORE_TOL, r
 
 
+@pytest.mark.parametrize("order", ["descending", "ascending"])
+def test_filter_strategy_survives_adversarial_item_order(order):
+    """The fused candidate filter takes its per-query threshold from the first items of the corpus.  Sorting the
+    corpus by one query's score makes that sample as unrepresentative as possible (threshold far too high /
+    far too low): the safety check must notice and the exact fallback must still return the right answer."""
+    cfg = CFG_8x8x32
+    N, B, k = 300_000, 4, 100
+    mol, _ = build_module(cfg, None, DEV, seed=21)
+    items, ids, q, _ = synthetic_inputs(cfg, N, B, 21, DEV)
+    ex0 = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=_lib.MODE_EXACT)
+    all0 = mol(q[:1], items.unsqueeze(0))[0][0]                      # (N,) exact scores of query 0
+    perm = torch.argsort(all0, descending=(order == "descending"))
+    items_p, ids_p = items[perm].contiguous(), ids[perm].contiguous()
+    top = MoLBruteForceTopK(mol, items_p.unsqueeze(0), ids_p.unsqueeze(0), mode=_lib.MODE_AUTO)
+    s, got = top(q, k=k)
+    s_ex, got_ex = ex0(q, k=k)
+    assert torch.equal(got, got_ex)
+    assert (s - s_ex).abs().max().item() < 1e-4
+
+
 # ------------------------------------------------------------------------------- tensor-core coarse pass
 @pytest.mark.parametrize(
     "cfg,N,B,seed",
