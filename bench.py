@@ -230,27 +230,24 @@ def main():
     out_i_host = torch.empty((B, k), dtype=torch.int64).pin_memory()
     tensor_path = engine.tensor_path_supported(weights.shape) and mode != _lib.MODE_EXACT
 
+    sharded = None
     if world > 1:
-        gather_s = torch.empty((world, B, k), dtype=torch.float32, device=dev)
-        gather_i = torch.empty((world, B, k), dtype=torch.int64, device=dev)
+        from rails_b200.indexing.sharded_top_k import ShardedMoLBruteForceTopK
+
+        # rank-local exact top-k of the shard -> ONE packed all-gather -> (R*k -> k) merge on every rank
+        sharded = ShardedMoLBruteForceTopK(top, hi - lo)
 
     def step_device():
-        s, i = engine.search(weights, index, wsp, q_dev, None, k, True, mode)
-        if world > 1:
-            dist.all_gather_into_tensor(gather_s, s)
-            dist.all_gather_into_tensor(gather_i, i)
-            s, i = engine.merge_topk(gather_s, gather_i, k)
-        return s, i
+        if world == 1:
+            return engine.search(weights, index, wsp, q_dev, None, k, True, mode)
+        return sharded(q_dev, k)
 
     def step_e2e():
         if world == 1:
             engine.search_host(weights, index, wsp, q_host, None, k, out_s_host, out_i_host, mode)
         else:
             qd = q_host.to(dev, non_blocking=True)
-            s, i = engine.search(weights, index, wsp, qd, None, k, True, mode)
-            dist.all_gather_into_tensor(gather_s, s)
-            dist.all_gather_into_tensor(gather_i, i)
-            s, i = engine.merge_topk(gather_s, gather_i, k)
+            s, i = sharded(qd, k)
             out_s_host.copy_(s, non_blocking=True)
             out_i_host.copy_(i, non_blocking=True)
             torch.cuda.current_stream().synchronize()

@@ -266,3 +266,46 @@ def test_coarse_pass_uneven_query_split_and_many_ctas():
         a = engine.score_all(w, idx, mol.workspace(dev), q, None, coarse=True)
         e = engine.score_all(w, idx, mol.workspace(dev), q, None)
         assert (a - e).abs().max().item() < 0.08
+
+
+# ------------------------------------------------------------------------------- multi-GPU (needs >= 2 devices)
+def _nccl_worker(rank, world, port, out):
+    import os
+
+    import torch.distributed as dist
+
+    from rails_b200.indexing.sharded_top_k import ShardedMoLBruteForceTopK, shard_range
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        cfg = CFG_8x8x32
+        N, B, k = 400_000, 16, 100
+        mol, _ = build_module(cfg, None, dev, seed=2)
+        items, ids, q, _ = synthetic_inputs(cfg, N, B, 2, dev)
+        lo, hi = shard_range(N, rank, world)
+        local = MoLBruteForceTopK(mol, items[lo:hi].unsqueeze(0), ids[lo:hi].unsqueeze(0))
+        s, i = ShardedMoLBruteForceTopK(local, hi - lo)(q, k)
+        full = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0))
+        rs, ri = full(q, k)
+        out[rank] = bool(torch.equal(i, ri)) and bool(torch.equal(s, rs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_topk_two_gpus_equals_unsharded():
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_nccl_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] is True and out[1] is True
