@@ -42,9 +42,13 @@ using namespace sm100;
 constexpr int kPQ = 8;          // query groups supported by this kernel
 constexpr int kH = 128;         // gating hidden width
 constexpr int kTile = 128;      // items per tile (= TMEM lanes)
-constexpr int kEpiThreads = 256;
-constexpr int kThreads = kEpiThreads + 4 * 32;  // + one control warpgroup (issuers, producer, one idle warp)
-constexpr int kEpiRegs = 208, kCtlRegs = 88;  // setmaxnreg split of the register file
+constexpr int kEpiThreads = 512;               // per TMEM slot: one E1/E3 warpgroup + one E2 warpgroup
+constexpr int kCtlWarp0 = kEpiThreads / 32;    // control warpgroup: issuer slot 0, issuer slot 1, TMA producer, (idle)
+constexpr int kThreads = kEpiThreads + 4 * 32;
+// setmaxnreg split of the 64K-register file (the kernel is compiled for 640 threads -> 96 registers at launch)
+// (setmaxnreg only redistributes the CTA's own launch allocation: 640 x 96 = 61440 registers)
+constexpr int kE13Regs = 160, kE2Regs = 56, kCtlRegs = 48;
+static_assert(256 * kE13Regs + 256 * kE2Regs + 128 * kCtlRegs <= kThreads * 96, "register pool over-committed");
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kK3 = kH + 16;    // K of the gate GEMM's TS part: hidden units + the ones block
 constexpr int kSmemLimit = 232448;
@@ -109,7 +113,7 @@ __host__ __device__ inline uint32_t nosw_off(int r, int k, int K) {
 
 struct Bars {
   uint64_t full[2], empty[2];
-  uint64_t q0_ready[2], e1_done[2], e2a_done[2], e2_done[2];
+  uint64_t q0_ready[2], e1_done[2], e2a_done[2], e2_done[2], gate_free[2];
   uint64_t log_full[2], hid_full[2], gate_full[2];
   uint32_t tmem_base;
 };
@@ -195,14 +199,15 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_init(&bars->e1_done[s], 128);
       mbar_init(&bars->e2a_done[s], 128);
       mbar_init(&bars->e2_done[s], 128);
+      mbar_init(&bars->gate_free[s], 128);
       mbar_init(&bars->log_full[s], 1);
       mbar_init(&bars->hid_full[s], 1);
       mbar_init(&bars->gate_full[s], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc<512>(&bars->tmem_base);
-  if (warp == 10 && lane == 0) {
+  if (warp == kCtlWarp0) tmem_alloc<512>(&bars->tmem_base);
+  if (warp == kCtlWarp0 + 2 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmGI);
   }
@@ -211,13 +216,14 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+
   // this CTA's flat range of (tile, query) units
   const int64_t F = (int64_t)(P.tile_end - P.tile_begin) * P.bc;
   const int64_t f0 = F * blockIdx.x / gridDim.x, f1 = F * (blockIdx.x + 1) / gridDim.x;
   const int t0 = P.tile_begin;
 
-  if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
-  if (warp == 10) {
+  if (warp >= kCtlWarp0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
+  if (warp == kCtlWarp0 + 2) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       TileWalk w(f0, f1, P.bc);
@@ -234,10 +240,10 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ++it;
       }
     }
-  } else if (warp == 8 || warp == 9) {
+  } else if (warp == kCtlWarp0 || warp == kCtlWarp0 + 1) {
     // =============================== MMA issuer of slot `wg` ===============================
     if (lane == 0) {
-      const int wg = warp - 8;
+      const int wg = warp - kCtlWarp0;
       constexpr uint32_t idesc1 = make_idesc_f16(128, 16);
       constexpr uint32_t idesc2 = make_idesc_f16(128, kH);
       constexpr uint32_t idesc3 = make_idesc_f16(128, L);
@@ -247,16 +253,21 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       uint32_t c1 = 0, c2 = 0;  // completed e1_done / e2_done phases of this slot
       bool first = true, pre_g1 = false;
 
+      // Descriptors advance by adding (bytes >> 4) to the 14-bit start-address field (no carry out of it: smem
+      // addresses are < 256 KB).  Loops stay rolled: the issuer has 48 registers and is not issue-bound.
+      const uint64_t dQ = make_smem_desc(sQa, 128, (C::K1 / 8) * 128, 0);
+      const uint64_t dW1 = make_smem_desc(sW1a, 128, (C::K2 / 8) * 128, 0);
+      const uint64_t dW2 = make_smem_desc(sW2a, 128, (kK3 / 8) * 128, 0);
+      const uint64_t dD = make_smem_desc(sDa, 128, (L / 8) * 128, 0);
       auto issue_g1 = [&](int s) __attribute__((always_inline)) {
         const uint32_t sXa = smem_u32(sX + s * C::X_BYTES);
-#pragma unroll
+#pragma unroll 1
         for (int g = 0; g < C::NG; ++g) {
-#pragma unroll
+#pragma unroll 1
           for (int ks = 0; ks < C::K1 / 16; ++ks) {
             const int e = g * C::K1 + ks * 16;  // first fp16 column of this K step in the item row
             const uint64_t da = make_smem_desc(sXa + (e / 64) * 16384 + (e % 64) * 2, 16, 1024, 2);
-            const uint64_t db = make_smem_desc(sQa + ks * 256, 128, (C::K1 / 8) * 128, 0);
-            umma_ss(base + kColLog + g * 16, da, db, idesc1, ks > 0);
+            umma_ss(base + kColLog + g * 16, da, dQ + (uint64_t)(ks * 16), idesc1, ks > 0);
           }
         }
         umma_commit(&bars->log_full[wg]);
@@ -288,15 +299,14 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           pre_g1 = false;
           const uint32_t sGIa = smem_u32(sGI + s * C::GI_BYTES);
           for (int j = 0; j < n; ++j) {
-            // ---- G2 (+ the next query's G1) once E1 has written A2 and staged the next query image
+            // ---- G2 (+ the next query's G1) once E1 has written A2 and staged the next query image.  HID is free:
+            //      this thread has already passed e2_done of the previous query.
             mbar_wait_sleep(&bars->e1_done[wg], c1 & 1u);
             ++c1;
             tc_fence_after();
-#pragma unroll
-            for (int ks = 0; ks < C::K2 / 16; ++ks) {
-              const uint64_t db = make_smem_desc(sW1a + ks * 256, 128, (C::K2 / 8) * 128, 0);
-              umma_ts(base + kColHid, base + kColLog + ks * 8, db, idesc2, ks > 0);
-            }
+#pragma unroll 1
+            for (int ks = 0; ks < C::K2 / 16; ++ks)
+              umma_ts(base + kColHid, base + kColLog + ks * 8, dW1 + (uint64_t)(ks * 16), idesc2, ks > 0);
             umma_commit(&bars->hid_full[wg]);
             if (j + 1 < n) {
               issue_g1(s);
@@ -307,31 +317,25 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               issue_g1(sn);
               pre_g1 = true;
             }
-            // ---- G3, first part, once E2 has written the first half of A3 (and staged nothing new: the diag
-            //      was staged by E3 of the previous query, whose reads of GATE are complete by now)
+            // ---- G3, first part: needs the first half of A3 (E2), the diag of this query staged and GATE released
+            //      by E3 of the previous query (gate_free; its first phase is arrived by the E1/E3 group's prologue)
             mbar_wait_sleep(&bars->e2a_done[wg], c2 & 1u);
+            mbar_wait_sleep(&bars->gate_free[wg], c2 & 1u);
             tc_fence_after();
-#pragma unroll
-            for (int ks = 0; ks < L / 16; ++ks) {  // GATE = GI_tile . diag(0.5 gq)
-              const uint64_t da = (L == 64) ? make_smem_desc(sGIa + ks * 32, 16, 1024, 2)
-                                            : make_smem_desc(sGIa + ks * 32, 16, 512, 4);
-              const uint64_t db = make_smem_desc(sDa + ks * 256, 128, (L / 8) * 128, 0);
-              umma_ss(base + kColGate, da, db, idesc3, ks > 0);
-            }
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {  // += A3[:, 0:64] . (0.5 W2[:, 0:64])^T
-              const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
-              umma_ts(base + kColGate, base + kColHid + ks * 8, db, idesc3, 1u);
-            }
+            const uint64_t dGI = (L == 64) ? make_smem_desc(sGIa, 16, 1024, 2) : make_smem_desc(sGIa, 16, 512, 4);
+#pragma unroll 1
+            for (int ks = 0; ks < L / 16; ++ks)  // GATE = GI_tile . diag(0.5 gq)
+              umma_ss(base + kColGate, dGI + (uint64_t)(ks * 2), dD + (uint64_t)(ks * 16), idesc3, ks > 0);
+#pragma unroll 1
+            for (int ks = 0; ks < 4; ++ks)  // += A3[:, 0:64] . (0.5 W2[:, 0:64])^T
+              umma_ts(base + kColGate, base + kColHid + ks * 8, dW2 + (uint64_t)(ks * 16), idesc3, 1u);
             // ---- G3, second part, once E2 has written all of A3
             mbar_wait_sleep(&bars->e2_done[wg], c2 & 1u);
             ++c2;
             tc_fence_after();
-#pragma unroll
-            for (int ks = 4; ks < kK3 / 16; ++ks) {  // += [A3[:, 64:128] | 1] . [0.5 W2[:, 64:128] | 0.5 b2]^T
-              const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
-              umma_ts(base + kColGate, base + kColHid + ks * 8, db, idesc3, 1u);
-            }
+#pragma unroll 1
+            for (int ks = 4; ks < kK3 / 16; ++ks)  // += [A3[:, 64:128] | 1] . [0.5 W2[:, 64:128] | 0.5 b2]^T
+              umma_ts(base + kColGate, base + kColHid + ks * 8, dW2 + (uint64_t)(ks * 16), idesc3, 1u);
             umma_commit(&bars->gate_full[wg]);
             if (j == n - 1) umma_commit(&bars->empty[s]);  // every MMA of this slot that reads stage s is issued
           }
@@ -341,16 +345,65 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ++it;
       }
     }
-  } else if (warp < 8) {
-    // =============================== epilogue warpgroups ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
-    const int wg = warp >> 2;                 // slot
+  } else if (warp < kCtlWarp0 && ((warp >> 2) & 1) == 1) {
+    // =============================== E2 warpgroup of slot `wg` ===============================
+    // hidden activations: HID (fp32) -> u -> h = u + u tanh(u) in packed half2 -> A3 (in place) + ones block
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kE2Regs));
+    const int wg = warp >> 3;
+    const uint32_t base = tmem + (uint32_t)wg * 256u + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t ones[8];
+    ones[0] = 0x00003C00u;  // {1.0h, 0}
+#pragma unroll
+    for (int i = 1; i < 8; ++i) ones[i] = 0u;
+    SlotSeq seq(f0, f1, P.bc, wg);
+    int tile = 0, q = 0;
+    uint32_t cnt = 0;
+    while (seq.next(tile, q)) {
+      mbar_wait_sleep(&bars->hid_full[wg], cnt & 1u);
+      tc_fence_after();
+      uint32_t va[16], vb[16];
+      auto act = [&](const uint32_t* v, uint32_t col) __attribute__((always_inline)) {
+        uint32_t hk[8];
+#pragma unroll
+        for (int j2 = 0; j2 < 8; ++j2) {
+          const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+          hk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
+        }
+        tmem_st_x8(base + col, hk);
+      };
+      // 8 chunks of 16 hidden units, loads one chunk ahead; A3 chunk c (8 columns) overwrites HID columns that
+      // chunk c/2 (already in registers) came from
+      tmem_ld_x16(base + kColHid, va);
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld_wait_bind16(va);
+        tmem_ld_x16(base + kColHid + 16 * (c + 1), vb);
+        act(va, kColHid + 8 * c);
+        tmem_ld_wait_bind16(vb);
+        if (c + 2 < 8) tmem_ld_x16(base + kColHid + 16 * (c + 2), va);
+        act(vb, kColHid + 8 * (c + 1));
+        if (c == 2) {  // first half of A3 (k < 64) is in TMEM: the issuer may start G3
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bars->e2a_done[wg]);
+        }
+      }
+      tmem_st_x8(base + kColHid + 64, ones);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bars->e2_done[wg]);
+      ++cnt;
+    }
+  } else if (warp < kCtlWarp0) {
+    // =============================== E1 / E3 warpgroup of slot `wg` ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kE13Regs));
+    const int wg = warp >> 3;                 // slot
     const int r = tid & 127;                  // item row within the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t base = tmem + (uint32_t)wg * 256u + lane_base;
     unsigned char* sQw = sQ + wg * C::Q_BYTES;
     __half* sDw = reinterpret_cast<__half*>(sD + wg * C::D_BYTES + (r < L ? nosw_off(r, r, L) : 0));
-    uint32_t cnt = 0;  // queries processed by this slot -> barrier parity
+    uint32_t cnt = 0;  // queries that went through E1 -> barrier parity
 
     // prefetched query data: image of the NEXT query to stage, 0.5*gq[r] of the query whose diag is staged next
     uint4 qv[C::QV];
@@ -375,11 +428,16 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       load_image(q);
       load_gq(q);
       store_image();
+      if (r < L) *sDw = gqv;  // diag of the first query: no G3 has run yet
       fence_proxy_async_smem();
       mbar_arrive(&bars->q0_ready[wg]);
+      mbar_arrive(&bars->gate_free[wg]);  // phase 0: GATE is free and the first diag is staged
     }
     bool have_n = have && seq.next(tile_n, q_n);
-    if (have_n) load_image(q_n);
+    if (have_n) {
+      load_image(q_n);
+      load_gq(q_n);
+    }
 
     uint32_t ones[8];
     ones[0] = 0x00003C00u;  // {1.0h, 0}
@@ -393,10 +451,9 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const float2 ec2 = make_float2(0.2426111251115799f, 0.2426111251115799f);
     const float2 ec3 = make_float2(0.0551716685295105f, 0.0551716685295105f);
 
-    // Stage order per slot: E1(j) -> E3(j-1) -> E2(j).  G2(j) runs on the tensor pipe behind E3(j-1) and
-    // G1(j+1) / G3(j) behind E2(j) / E1(j+1), so the warpgroup rarely waits for an MMA.  The logits of two
-    // queries are live at once, as packed fp16 pairs (pkA / pkB alternate).
-    auto e1 = [&](uint32_t (&pk)[L / 2], bool stage_diag) __attribute__((always_inline)) {
+    // Stage order of this group: E1(j) -> E3(j-1).  E2(j) runs concurrently in the slot's other warpgroup, the MMAs
+    // behind both.  The logits of two queries are live at once, as packed fp16 pairs (pkA / pkB alternate).
+    auto e1 = [&](uint32_t (&pk)[L / 2]) __attribute__((always_inline)) {
       mbar_wait_sleep(&bars->log_full[wg], cnt & 1u);
       tc_fence_after();
       {
@@ -405,7 +462,6 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if constexpr (L == 64) tmem_ld_x32(base + kColLog + 32, lb);
         // G1 of this query is complete: its image buffer is free for the next query
         if (have_n) store_image();
-        if (stage_diag && r < L) *sDw = gqv;  // first query only: no earlier G3 can be reading the diag buffer
         fence_proxy_async_smem();
         tmem_ld_wait_bind32(la);
 #pragma unroll
@@ -429,46 +485,12 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_arrive(&bars->e1_done[wg]);
     };
 
-    auto e2 = [&]() __attribute__((always_inline)) {
-      mbar_wait_sleep(&bars->hid_full[wg], cnt & 1u);
-      tc_fence_after();
-      uint32_t va[32], vb[32];
-      auto act = [&](const uint32_t* v, uint32_t col) __attribute__((always_inline)) {
-        uint32_t hk[16];
-#pragma unroll
-        for (int j2 = 0; j2 < 16; ++j2) {
-          const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
-          hk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
-        }
-        tmem_st_x16(base + col, hk);
-      };
-      tmem_ld_x32(base + kColHid, va);
-      tmem_ld_wait_bind32(va);
-      tmem_ld_x32(base + kColHid + 32, vb);
-      act(va, kColHid);
-      tmem_ld_wait_bind32(vb);
-      tmem_ld_x32(base + kColHid + 64, va);
-      act(vb, kColHid + 16);
-      tmem_st_wait();  // first half of A3 (k < 64) is in TMEM: the issuer may start G3
-      tc_fence_before();
-      mbar_arrive(&bars->e2a_done[wg]);
-      tmem_ld_wait_bind32(va);
-      tmem_ld_x32(base + kColHid + 96, vb);
-      act(va, kColHid + 32);
-      tmem_ld_wait_bind32(vb);
-      act(vb, kColHid + 48);
-      tmem_st_x8(base + kColHid + 64, ones);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&bars->e2_done[wg]);
-    };
-
-    // E3 of the query processed one step earlier (barrier phase cnt - 1); also stages the diag of the query whose
-    // E2 follows (its G3 is issued after that E2; the previous G3 is complete once gate_full has fired).
-    auto e3 = [&](const uint32_t (&pk)[L / 2], int tile_p, int q_p, bool stage_diag) __attribute__((always_inline)) {
+    // E3 of query (tile_p, q_p) (gate_full phase `par`).  Once GATE is in registers it stages the diag of the next
+    // query in sequence (if any: its G3 is the next writer of GATE and the next reader of the diag) and releases both.
+    auto e3 = [&](const uint32_t (&pk)[L / 2], int tile_p, int q_p, uint32_t par, bool stage_diag) __attribute__((always_inline)) {
       // the filter threshold of this query: loaded now, used after the weighted sum
       const float thr_q = P.thr ? __ldg(P.thr + (size_t)q_p * P.thr_stride) : -CUDART_INF_F;
-      mbar_wait_sleep(&bars->gate_full[wg], (cnt - 1u) & 1u);
+      mbar_wait_sleep(&bars->gate_full[wg], par);
       tc_fence_after();
       float2 num[4], den[4];
 #pragma unroll
@@ -505,17 +527,19 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       };
       tmem_ld_x32(base + kColGate, va);
+      if constexpr (L == 64) tmem_ld_x32(base + kColGate + 32, vb);
       if (stage_diag) {
-        if (r < L) *sDw = gqv;
+        if (r < L) *sDw = gqv;  // G3 of this query is complete (gate_full): the diag buffer is free
         fence_proxy_async_smem();
       }
       tmem_ld_wait_bind32(va);
-      if constexpr (L == 64) tmem_ld_x32(base + kColGate + 32, vb);
-      gate(va, pk);
-      if constexpr (L == 64) {
-        tmem_ld_wait_bind32(vb);
-        gate(vb, pk + 16);
+      if constexpr (L == 64) tmem_ld_wait_bind32(vb);
+      if (stage_diag) {
+        tc_fence_before();
+        mbar_arrive(&bars->gate_free[wg]);
       }
+      gate(va, pk);
+      if constexpr (L == 64) gate(vb, pk + 16);
       const float2 n2 = __fadd2_rn(__fadd2_rn(num[0], num[1]), __fadd2_rn(num[2], num[3]));
       const float2 d2 = __fadd2_rn(__fadd2_rn(den[0], den[1]), __fadd2_rn(den[2], den[3]));
       const float score = __fdividef(n2.x + n2.y, d2.x + d2.y);
@@ -535,19 +559,20 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint32_t pkA[L / 2], pkB[L / 2];
     int tile_p = 0, q_p = 0;
     bool have_p = false;
-    // one step: E1(cur) -> E3(prev) -> E2(cur); then advance the query window
+    // one step: E1(cur) -> E3(prev); then advance the query window.
+    // gqv holds 0.5*gq of the CURRENT query's successor... see the load schedule below:
+    //   diag(j) is staged inside E3(j-1) (after gate_full(j-1)), so gq(j) must be in `gqv` at that point: it is
+    //   loaded right after diag(j-1) was staged, one step earlier.
     auto step = [&](uint32_t (&pk_cur)[L / 2], const uint32_t (&pk_prev)[L / 2]) __attribute__((always_inline)) {
-      e1(pk_cur, !have_p);
-      // prefetch: gq of the next query (its diag is staged one step later), image of the one after
+      e1(pk_cur);
       int tile_nn = 0, q_nn = 0;
       const bool have_nn = have_n && seq.next(tile_nn, q_nn);
+      if (have_nn) load_image(q_nn);  // image of the query after next (qv was stored to smem inside e1)
       if (have_p) {
-        // gqv currently holds this query's 0.5*gq (loaded one step ago): E3(prev) stages it, then it is reloaded
-        e3(pk_prev, tile_p, q_p, true);
+        // E3(prev) stages diag(cur) from gqv, which currently holds gq(cur)
+        e3(pk_prev, tile_p, q_p, (cnt - 1u) & 1u, true);
+        if (have_n) load_gq(q_n);  // gq(next), staged by the next step's E3
       }
-      if (have_n) load_gq(q_n);
-      if (have_nn) load_image(q_nn);
-      e2();
       ++cnt;
       tile_p = tile;
       q_p = q;
@@ -562,14 +587,12 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     while (have) {
       step(pkA, pkB);
       if (!have) {
-        e3(pkA, tile_p, q_p, false);
-        have_p = false;
+        e3(pkA, tile_p, q_p, (cnt - 1u) & 1u, false);
         break;
       }
       step(pkB, pkA);
       if (!have) {
-        e3(pkB, tile_p, q_p, false);
-        have_p = false;
+        e3(pkB, tile_p, q_p, (cnt - 1u) & 1u, false);
         break;
       }
     }
@@ -577,7 +600,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<512>(tmem);
+  if (warp == kCtlWarp0) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
