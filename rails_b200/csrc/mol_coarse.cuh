@@ -25,6 +25,7 @@ struct CoarseOut {
   int cand_cap;
 };
 
+void* coarse_trace_buffer();  // debug (MOL_TRACE builds): device buffer for stage timestamps, or nullptr
 bool coarse_supported(const mol_shape_t& s);
 void coarse_plan(const mol_shape_t& s, int chunk, Arena& a, CoarseWs* ws);
 // weight images (once per search call)

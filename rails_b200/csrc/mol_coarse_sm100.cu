@@ -88,7 +88,18 @@ struct CoarseCfg {
   static_assert(QV >= 1, "query image smaller than one uint4 per thread");
 };
 
+#ifdef MOL_TRACE
+#define TR(role, ev, idx)                                                                        \
+  do {                                                                                           \
+    if (blockIdx.x == 0 && P.trace && (idx) < 256u && (threadIdx.x & 31) == 0)                    \
+      P.trace[((role) * 256 + (idx)) * 8 + (ev)] = clock64();                                     \
+  } while (0)
+#else
+#define TR(role, ev, idx) do {} while (0)
+#endif
+
 struct CoarseParams {
+  long long* trace;
   const uint8_t* w1_img;
   const uint8_t* w2_img;
   const uint8_t* q_rec;   // (bc, QREC_BYTES)
@@ -242,7 +253,11 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else if (warp == kCtlWarp0 || warp == kCtlWarp0 + 1) {
     // =============================== MMA issuer of slot `wg` ===============================
-    if (lane == 0) {
+    // The whole warp runs this loop converged (all lanes wait, all lanes compute the warp-uniform descriptors);
+    // only the tcgen05 instructions themselves are issued by one elected lane.  Issuing from inside an
+    // `if (lane == 0)` region makes ptxas wrap every MMA in a uniform-register "waterfall" (~150 clk per MMA,
+    // measured), which starved the tensor pipe.
+    {
       const int wg = warp - kCtlWarp0;
       constexpr uint32_t idesc1 = make_idesc_f16(128, 16);
       constexpr uint32_t idesc2 = make_idesc_f16(128, kH);
@@ -253,24 +268,22 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       uint32_t c1 = 0, c2 = 0;  // completed e1_done / e2_done phases of this slot
       bool first = true, pre_g1 = false;
 
-      // Descriptors advance by adding (bytes >> 4) to the 14-bit start-address field (no carry out of it: smem
-      // addresses are < 256 KB).  Loops stay rolled: the issuer has 48 registers and is not issue-bound.
-      const uint64_t dQ = make_smem_desc(sQa, 128, (C::K1 / 8) * 128, 0);
-      const uint64_t dW1 = make_smem_desc(sW1a, 128, (C::K2 / 8) * 128, 0);
-      const uint64_t dW2 = make_smem_desc(sW2a, 128, (kK3 / 8) * 128, 0);
-      const uint64_t dD = make_smem_desc(sDa, 128, (L / 8) * 128, 0);
       auto issue_g1 = [&](int s) __attribute__((always_inline)) {
         const uint32_t sXa = smem_u32(sX + s * C::X_BYTES);
-#pragma unroll 1
-        for (int g = 0; g < C::NG; ++g) {
-#pragma unroll 1
-          for (int ks = 0; ks < C::K1 / 16; ++ks) {
-            const int e = g * C::K1 + ks * 16;  // first fp16 column of this K step in the item row
-            const uint64_t da = make_smem_desc(sXa + (e / 64) * 16384 + (e % 64) * 2, 16, 1024, 2);
-            umma_ss(base + kColLog + g * 16, da, dQ + (uint64_t)(ks * 16), idesc1, ks > 0);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int g = 0; g < C::NG; ++g) {
+#pragma unroll
+            for (int ks = 0; ks < C::K1 / 16; ++ks) {
+              const int e = g * C::K1 + ks * 16;  // first fp16 column of this K step in the item row
+              const uint64_t da = make_smem_desc(sXa + (e / 64) * 16384 + (e % 64) * 2, 16, 1024, 2);
+              const uint64_t db = make_smem_desc(sQa + ks * 256, 128, (C::K1 / 8) * 128, 0);
+              umma_ss(base + kColLog + g * 16, da, db, idesc1, ks > 0);
+            }
           }
+          umma_commit(&bars->log_full[wg]);
         }
-        umma_commit(&bars->log_full[wg]);
+        __syncwarp();
       };
 
       TileWalk w(f0, f1, P.bc);
@@ -286,7 +299,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const bool have_next = wn.next();
         const int n_next = have_next ? wn.n_mine(wg) : 0;
         if (n == 0) {
-          mbar_arrive(&bars->empty[s]);
+          if (lane == 0) mbar_arrive(&bars->empty[s]);
         } else {
           if (!pre_g1) {
             if (first) {
@@ -300,14 +313,21 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const uint32_t sGIa = smem_u32(sGI + s * C::GI_BYTES);
           for (int j = 0; j < n; ++j) {
             // ---- G2 (+ the next query's G1) once E1 has written A2 and staged the next query image.  HID is free:
-            //      this thread has already passed e2_done of the previous query.
+            //      this warp has already passed e2_done of the previous query.
+            if (wg == 0) TR(2, 0, c1);
             mbar_wait_sleep(&bars->e1_done[wg], c1 & 1u);
+            if (wg == 0) TR(2, 1, c1);
             ++c1;
             tc_fence_after();
-#pragma unroll 1
-            for (int ks = 0; ks < C::K2 / 16; ++ks)
-              umma_ts(base + kColHid, base + kColLog + ks * 8, dW1 + (uint64_t)(ks * 16), idesc2, ks > 0);
-            umma_commit(&bars->hid_full[wg]);
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int ks = 0; ks < C::K2 / 16; ++ks) {
+                const uint64_t db = make_smem_desc(sW1a + ks * 256, 128, (C::K2 / 8) * 128, 0);
+                umma_ts(base + kColHid, base + kColLog + ks * 8, db, idesc2, ks > 0);
+              }
+              umma_commit(&bars->hid_full[wg]);
+            }
+            __syncwarp();
             if (j + 1 < n) {
               issue_g1(s);
             } else if (n_next > 0 && C::STAGES > 1) {  // (single stage: the next tile cannot land before this one is released)
@@ -317,27 +337,45 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               issue_g1(sn);
               pre_g1 = true;
             }
+            if (wg == 0) TR(2, 2, c2);
             // ---- G3, first part: needs the first half of A3 (E2), the diag of this query staged and GATE released
             //      by E3 of the previous query (gate_free; its first phase is arrived by the E1/E3 group's prologue)
             mbar_wait_sleep(&bars->e2a_done[wg], c2 & 1u);
             mbar_wait_sleep(&bars->gate_free[wg], c2 & 1u);
             tc_fence_after();
-            const uint64_t dGI = (L == 64) ? make_smem_desc(sGIa, 16, 1024, 2) : make_smem_desc(sGIa, 16, 512, 4);
-#pragma unroll 1
-            for (int ks = 0; ks < L / 16; ++ks)  // GATE = GI_tile . diag(0.5 gq)
-              umma_ss(base + kColGate, dGI + (uint64_t)(ks * 2), dD + (uint64_t)(ks * 16), idesc3, ks > 0);
-#pragma unroll 1
-            for (int ks = 0; ks < 4; ++ks)  // += A3[:, 0:64] . (0.5 W2[:, 0:64])^T
-              umma_ts(base + kColGate, base + kColHid + ks * 8, dW2 + (uint64_t)(ks * 16), idesc3, 1u);
+            if (wg == 0) TR(2, 3, c2);
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int ks = 0; ks < L / 16; ++ks) {  // GATE = GI_tile . diag(0.5 gq)
+                const uint64_t da = (L == 64) ? make_smem_desc(sGIa + ks * 32, 16, 1024, 2)
+                                              : make_smem_desc(sGIa + ks * 32, 16, 512, 4);
+                const uint64_t db = make_smem_desc(sDa + ks * 256, 128, (L / 8) * 128, 0);
+                umma_ss(base + kColGate, da, db, idesc3, ks > 0);
+              }
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {  // += A3[:, 0:64] . (0.5 W2[:, 0:64])^T
+                const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
+                umma_ts(base + kColGate, base + kColHid + ks * 8, db, idesc3, 1u);
+              }
+            }
+            __syncwarp();
+            if (wg == 0) TR(2, 4, c2);
             // ---- G3, second part, once E2 has written all of A3
             mbar_wait_sleep(&bars->e2_done[wg], c2 & 1u);
+            if (wg == 0) TR(2, 5, c2);
             ++c2;
             tc_fence_after();
-#pragma unroll 1
-            for (int ks = 4; ks < kK3 / 16; ++ks)  // += [A3[:, 64:128] | 1] . [0.5 W2[:, 64:128] | 0.5 b2]^T
-              umma_ts(base + kColGate, base + kColHid + ks * 8, dW2 + (uint64_t)(ks * 16), idesc3, 1u);
-            umma_commit(&bars->gate_full[wg]);
-            if (j == n - 1) umma_commit(&bars->empty[s]);  // every MMA of this slot that reads stage s is issued
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int ks = 4; ks < kK3 / 16; ++ks) {  // += [A3[:, 64:128] | 1] . [0.5 W2[:, 64:128] | 0.5 b2]^T
+                const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
+                umma_ts(base + kColGate, base + kColHid + ks * 8, db, idesc3, 1u);
+              }
+              umma_commit(&bars->gate_full[wg]);
+              if (j == n - 1) umma_commit(&bars->empty[s]);  // every MMA of this slot that reads stage s is issued
+            }
+            __syncwarp();
+            if (wg == 0) TR(2, 6, c2 - 1);
           }
         }
         w = wn;
@@ -359,15 +397,21 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     int tile = 0, q = 0;
     uint32_t cnt = 0;
     while (seq.next(tile, q)) {
+      if (warp == 4) TR(1, 0, cnt);
       mbar_wait_sleep(&bars->hid_full[wg], cnt & 1u);
       tc_fence_after();
+      if (warp == 4) TR(1, 1, cnt);
       uint32_t va[16], vb[16];
       auto act = [&](const uint32_t* v, uint32_t col) __attribute__((always_inline)) {
         uint32_t hk[8];
 #pragma unroll
         for (int j2 = 0; j2 < 8; ++j2) {
           const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+#ifdef MOL_ABLATE_E2
+          hk[j2] = fma_f16x2(u2, u2, u2);
+#else
           hk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
+#endif
         }
         tmem_st_x8(base + col, hk);
       };
@@ -386,12 +430,14 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&bars->e2a_done[wg]);
+          if (warp == 4) TR(1, 2, cnt);
         }
       }
       tmem_st_x8(base + kColHid + 64, ones);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bars->e2_done[wg]);
+      if (warp == 4) TR(1, 3, cnt);
       ++cnt;
     }
   } else if (warp < kCtlWarp0) {
@@ -454,8 +500,10 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // Stage order of this group: E1(j) -> E3(j-1).  E2(j) runs concurrently in the slot's other warpgroup, the MMAs
     // behind both.  The logits of two queries are live at once, as packed fp16 pairs (pkA / pkB alternate).
     auto e1 = [&](uint32_t (&pk)[L / 2]) __attribute__((always_inline)) {
+      if (warp == 0) TR(0, 0, cnt);
       mbar_wait_sleep(&bars->log_full[wg], cnt & 1u);
       tc_fence_after();
+      if (warp == 0) TR(0, 1, cnt);
       {
         uint32_t la[32], lb[32];
         tmem_ld_x32(base + kColLog, la);
@@ -483,6 +531,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bars->e1_done[wg]);
+      if (warp == 0) TR(0, 2, cnt);
     };
 
     // E3 of query (tile_p, q_p) (gate_full phase `par`).  Once GATE is in registers it stages the diag of the next
@@ -490,8 +539,10 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     auto e3 = [&](const uint32_t (&pk)[L / 2], int tile_p, int q_p, uint32_t par, bool stage_diag) __attribute__((always_inline)) {
       // the filter threshold of this query: loaded now, used after the weighted sum
       const float thr_q = P.thr ? __ldg(P.thr + (size_t)q_p * P.thr_stride) : -CUDART_INF_F;
+      if (warp == 0) TR(0, 3, cnt - 1u);
       mbar_wait_sleep(&bars->gate_full[wg], par);
       tc_fence_after();
+      if (warp == 0) TR(0, 4, cnt - 1u);
       float2 num[4], den[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) num[i] = den[i] = make_float2(0.f, 0.f);
@@ -505,7 +556,11 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             u.y = fminf(u.y, kGateClamp);
           }
           const float2 a = __fmul2_rn(u, l2e2);
+#ifdef MOL_ABLATE_E3
+          const float2 t = u;
+#else
           const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+#endif
           const float2 x = __ffma2_rn(a, t, a);  // w * log2(e), in [-0.41, 116]
           float2 e;
           if ((j2 & 3) < kEx2EmuOf4) {
@@ -520,7 +575,11 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             e.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(m.x) << 23));
             e.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(m.y) << 23));
           } else {
+#ifdef MOL_ABLATE_E3
+            e = x;
+#else
             e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+#endif
           }
           den[j2 & 3] = __fadd2_rn(den[j2 & 3], e);
           num[j2 & 3] = __ffma2_rn(e, __half22float2(*reinterpret_cast<const __half2*>(&lgc[j2])), num[j2 & 3]);
@@ -543,6 +602,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const float2 n2 = __fadd2_rn(__fadd2_rn(num[0], num[1]), __fadd2_rn(num[2], num[3]));
       const float2 d2 = __fadd2_rn(__fadd2_rn(den[0], den[1]), __fadd2_rn(den[2], den[3]));
       const float score = __fdividef(n2.x + n2.y, d2.x + d2.y);
+      if (warp == 0) TR(0, 5, cnt - 1u);
       const int64_t item = (int64_t)(t0 + tile_p) * kTile + r;
       if (item < P.N) {
         if (P.scores) P.scores[(size_t)q_p * P.ld + ((int64_t)tile_p * kTile + r)] = score;
@@ -736,6 +796,10 @@ static int encode_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t r
   return MOL_OK;
 }
 
+static void* g_trace = nullptr;
+void* coarse_trace_buffer() { return g_trace; }
+extern "C" void mol_debug_set_trace(void* p) { g_trace = p; }
+
 template <int PX, int DD>
 static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, const float* qsub,
                          const float* gq, int bc, const CoarseOut& out, cudaStream_t st) {
@@ -751,6 +815,7 @@ static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const Coar
   MOL_TRY(encode_2d(&tmGI, ix.gi_half, C::L, (uint64_t)Np, C::L, kTile,
                     C::L == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
   CoarseParams P;
+  P.trace = (long long*)coarse_trace_buffer();
   P.w1_img = ws.w1_img;
   P.w2_img = ws.w2_img;
   P.q_rec = ws.q_rec;

@@ -297,6 +297,111 @@ __global__ void probe_pipe_kernel(int which, int iters, float seed, float* sink,
   if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Probe 5: TMEM load / store throughput.  Every warp of the block issues `iters` back-to-back
+// tcgen05.ld (which 0: 32x32b.x32, 1: .x16) or tcgen05.st (2: .x32) on its own lane quarter.
+// ------------------------------------------------------------------------------------------------
+__global__ void probe_tmem_kernel(int which, int iters, float* sink, long long* cycles) {
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) & 3) * 64u;
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = threadIdx.x + i;
+  tmem_st_x32(base, v);
+  tmem_st_x32(base + 32, v);
+  tmem_st_wait();
+  __syncthreads();
+  long long t0 = clock64();
+  uint32_t acc = 0;
+  for (int i = 0; i < iters; ++i) {
+    if (which == 0) {
+      tmem_ld_x32(base + (i & 1) * 32, v);
+      tmem_ld_wait();
+      acc += v[0] ^ v[31];
+    } else if (which == 1) {
+      tmem_ld_x16(base + (i & 3) * 16, v);
+      tmem_ld_wait();
+      acc += v[0] ^ v[15];
+    } else if (which == 2) {
+      v[0] = acc + i;
+      tmem_st_x32(base + (i & 1) * 32, v);
+      tmem_st_wait();
+    } else {  // 4 loads in flight before one wait
+      uint32_t w[32];
+      tmem_ld_x16(base, v);
+      tmem_ld_x16(base + 16, v + 16);
+      tmem_ld_x16(base + 32, w);
+      tmem_ld_x16(base + 48, w + 16);
+      tmem_ld_wait();
+      acc += v[0] ^ v[31] ^ w[0] ^ w[31];
+    }
+  }
+  long long t1 = clock64();
+  __syncthreads();
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = __uint_as_float(acc);
+  if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_slot);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Probe 6: tcgen05.mma issue / execution cost per instruction.  One converged warp issues `iters` MMAs
+// (M = 128, K = 16, N = n) back to back, then commits.  mode 0: SS (A, B from smem), 1: TS (A from TMEM).
+// out: cycles[0] = issue loop, cycles[1] = until the commit's mbarrier fires.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void probe_mma_rate_kernel(int mode, int iters, long long* cycles) {
+  extern __shared__ unsigned char smem_raw2[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (16384 + 256 * 32) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    const uint32_t sA = smem_u32(smem), sB = smem_u32(smem + 16384);
+    const uint64_t da = make_smem_desc(sA, 16, 1024, 2);
+    const uint64_t db = make_smem_desc(sB, 128, 256, 0);
+    long long t0 = clock64();
+    if (elect_one_sync()) {
+      for (int i = 0; i < iters; ++i) {
+        if (mode == 0) umma_ss(tmem + 256, da, db, idesc, 1u);
+        else umma_ts(tmem + 256, tmem, db, idesc, 1u);
+      }
+      umma_commit(&bar);
+    }
+    __syncwarp();
+    long long t1 = clock64();
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+      cycles[0] = t1 - t0;
+      cycles[1] = t2 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -373,6 +478,33 @@ int probe_pipe(int which, int iters, int threads, int blocks, float* sink, long 
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     fprintf(stderr, "probe_pipe: %s\n", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+int probe_tmem(int which, int iters, int threads, int blocks, float* sink, long long* cycles) {
+  probe_tmem_kernel<<<blocks, threads>>>(which, iters, sink, cycles);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "probe_tmem: %s\n", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+int probe_mma_rate(int n, int mode, int iters, int blocks, long long* cycles) {
+  size_t smem = 16384 + 256 * 32 + 2048;
+#define RUNR(NN)                                                                                             \
+  {                                                                                                          \
+    cudaFuncSetAttribute(probe_mma_rate_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    probe_mma_rate_kernel<NN><<<blocks, 128, smem>>>(mode, iters, cycles);                                   \
+  }
+  if (n == 16) RUNR(16) else if (n == 32) RUNR(32) else if (n == 64) RUNR(64) else if (n == 128) RUNR(128) else if (n == 256) RUNR(256) else return -1;
+#undef RUNR
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "probe_mma_rate: %s\n", cudaGetErrorString(e));
     return 1;
   }
   return 0;

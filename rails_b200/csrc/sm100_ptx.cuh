@@ -48,6 +48,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Blocking wait for control warps: the hardware may suspend the thread until the phase completes
 // (or the hint, in ns, elapses), so a waiting issuer does not burn issue slots of its SM sub-partition.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+#ifdef MOL_SPIN_WAIT
+  mbar_wait(bar, parity);
+  return;
+#endif
   uint32_t ok;
   do {
     asm volatile(
@@ -121,6 +125,19 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4)                      // D format  = F32   (A/B format fields 0 = F16)
          | ((uint32_t)(N >> 3) << 17)   // N >> 3
          | ((uint32_t)(M >> 4) << 24);  // M >> 4
+}
+
+// One lane of a converged warp (warp-uniform predicate: lets ptxas keep the MMA operands in uniform registers).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---------------------------------------------------------------- tcgen05.mma (single thread issues)

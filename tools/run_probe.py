@@ -91,12 +91,42 @@ def pipe():
                               "thread_instr_per_clk_per_sm": iters * per_iter * threads / c}))
 
 
+def tmem():
+    names = [("ld.x32 + wait", 4096), ("ld.x16 + wait", 2048), ("st.x32 + wait", 4096), ("4 x ld.x16 then wait", 8192)]
+    sink = torch.empty(148 * 1024, device="cuda")
+    cyc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    iters = 2048
+    for which, (name, bytes_per_warp_iter) in enumerate(names):
+        for threads in (128, 256, 512):
+            lib.probe_tmem(which, 16, threads, 148, ptr(sink), ptr(cyc))
+            rc = lib.probe_tmem(which, iters, threads, 148, ptr(sink), ptr(cyc))
+            c = cyc.item()
+            print(json.dumps({"probe": "tmem", "op": name, "threads_per_sm": threads, "rc": rc, "cycles": c,
+                              "cycles_per_iter": c / iters, "bytes_per_clk_per_sm": iters * bytes_per_warp_iter * (threads // 32) / c}))
+
+
+def mma_rate():
+    cyc = torch.zeros(2, dtype=torch.int64, device="cuda")
+    iters = 256
+    for mode, mname in ((0, "SS"), (1, "TS")):
+        for n in (16, 32, 64, 128, 256):
+            lib.probe_mma_rate(n, mode, 8, 148, ptr(cyc))
+            rc = lib.probe_mma_rate(n, mode, iters, 148, ptr(cyc))
+            c = cyc.tolist()
+            print(json.dumps({"probe": "mma_rate", "mode": mname, "N": n, "rc": rc, "issue_clk_per_mma": c[0] / iters,
+                              "total_clk_per_mma": c[1] / iters, "floor": 128 * n / 256}))
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     if what == "mma":
         mma(int(sys.argv[2]))
     elif what == "tma":
         tma()
+    elif what == "mma_rate":
+        mma_rate()
+    elif what == "tmem":
+        tmem()
     elif what == "pipe":
         pipe()
     else:
