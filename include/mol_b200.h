@@ -163,6 +163,26 @@ int mol_topk(const float* scores, int64_t n, int64_t ld, int32_t B, int32_t k, c
              float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
              mol_stream_t stream);
 
+/* ---- callers / siblings of the path ---- */
+
+/* Seen-item masking + back-fill of CandidateIndex.get_top_k_outputs (indexing/candidate_index.py:155-178):
+ * scores / ids (B, k') sorted by score (the over-fetched top-k'), invalid_ids (B, n_invalid) int64; keeps per row the
+ * first k ids not in the row's invalid list, back-fills short rows with their first invalid entries, preserves
+ * rank order.  No workspace, no host sync (the reference syncs in torch.nonzero). */
+int mol_select_valid(const float* scores, const int64_t* ids, const int64_t* invalid_ids, int32_t B,
+                     int32_t k_prime, int32_t n_invalid, int32_t k, float* out_scores, int64_t* out_ids,
+                     mol_stream_t stream);
+
+/* MIPSBruteForceTopK.forward (rails/indexing/mips_top_k.py:74-81): fp32 q . items^T, top-k, id gather.
+ * items (N, D) fp32 device, item_ids (N) int64 or NULL, queries (B, D) fp32. */
+int mol_mips_workspace_bytes(int64_t num_items, int32_t B, int32_t k, size_t* bytes);
+int mol_mips_search(const float* items, const int64_t* item_ids, const float* queries, int64_t num_items,
+                    int32_t D, int32_t B, int32_t k, float* out_scores, int64_t* out_ids, void* workspace,
+                    size_t workspace_bytes, mol_stream_t stream);
+/* DotProductSimilarity.forward, (1, X, D) branch (rails/similarities/dot_product_similarity_fn.py:46-51): (B, N) fp32. */
+int mol_dot_scores(const float* items, const float* queries, int64_t num_items, int32_t D, int32_t B,
+                   float* out_scores, mol_stream_t stream);
+
 /* Optional CUDA-event timing of the dominant scoring kernel (the tcgen05 coarse pass, or the fp32
  * kernel in MOL_MODE_EXACT) on the stream it is launched on: enable, run searches, collect the summed
  * device time and the number of timed launches (collect synchronises on the recorded events). */

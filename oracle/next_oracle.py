@@ -1,0 +1,37 @@
+"""CPU oracle for the callers / siblings of the MoL top-k path.  TEST INFRASTRUCTURE ONLY.
+
+Restates, with torch CPU ops,
+  * the seen-item masking + back-fill of ``CandidateIndex.get_top_k_outputs``
+    (reference indexing/candidate_index.py:155-178), and
+  * ``MIPSBruteForceTopK.forward`` (reference rails/indexing/mips_top_k.py:74-81).
+Pinned against outputs of the unmodified reference classes by ``oracle/gen_golden_next.py`` ->
+``tests/golden/next_*.npz`` (``tests/test_next_oracle_golden.py``).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+
+def select_valid(
+    top_k_prime_scores: torch.Tensor, top_k_prime_ids: torch.Tensor, invalid_ids: torch.Tensor, k: int
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(B, k') score-sorted candidates + (B, N0) invalid ids -> (scores (B, k), ids (B, k)).  candidate_index.py:155-178."""
+    is_seen = (top_k_prime_ids.unsqueeze(2) == invalid_ids.unsqueeze(1)).max(2)[0]  # :156
+    valid = ~is_seen
+    valid = torch.logical_and(valid, torch.cumsum(valid.int(), dim=1) <= k)  # :158
+    inv = ~valid  # :163 (seen ids and valid ids beyond the first k)
+    gap = k - valid.int().sum(1, keepdim=True)  # :164
+    valid = torch.logical_or(valid, torch.logical_and(inv, torch.cumsum(inv.int(), dim=1) <= gap))  # :165-171
+    offsets = torch.nonzero(valid, as_tuple=True)[1].view(-1, k)  # :174
+    return torch.gather(top_k_prime_scores, 1, offsets), torch.gather(top_k_prime_ids, 1, offsets)
+
+
+def mips_top_k(
+    query_embeddings: torch.Tensor, item_embeddings: torch.Tensor, item_ids: torch.Tensor, k: int
+) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(B, D), (N, D), (N,) -> (top scores (B, k), top ids (B, k), all logits (B, N)).  mips_top_k.py:74-81."""
+    all_logits = torch.mm(query_embeddings, item_embeddings.t())
+    s, i = torch.topk(all_logits, dim=1, k=k, sorted=True, largest=True)
+    return s, item_ids.reshape(-1)[i], all_logits

@@ -8,12 +8,13 @@
 // (B, N, H) hidden activations and (B, N, L) gates never leave the SM.  Its output only RANKS
 // candidates; final scores come from the fp32 rescoring pass (mol_exact.cu).
 //
-// Mapping (one persistent CTA per SM, 384 threads; setmaxnreg gives the epilogue warpgroups 208 registers):
-//   warps 0-3   epilogue warpgroup 0  (TMEM slot 0, even queries of the tile's query range)
-//   warps 4-7   epilogue warpgroup 1  (TMEM slot 1, odd queries)
-//   warp 8/9    MMA issuer of slot 0 / slot 1: one thread, blocking mbarrier waits in the slot's fixed order
-//   warp 10     TMA producer: item tile (128 items x P_X*d fp16, SWIZZLE_128B boxes) + the tile's GI rows,
-//               double-buffered through full/empty mbarriers.
+// Mapping (one persistent CTA per SM, 640 threads = 5 warpgroups; setmaxnreg splits the register file 160/56/48):
+//   per TMEM slot s (2 slots, 256 columns each; slot 0 takes the even queries of a tile's range, slot 1 the odd ones):
+//     warps 8s+0..3   E1/E3 warpgroup: logits -> fp16 operand (E1), gate -> softmax-weighted score -> output (E3)
+//     warps 8s+4..7   E2 warpgroup   : hidden pre-activations -> silu -> fp16 operand
+//   warp 16/17  MMA issuer of slot 0 / 1: the warp runs converged, one elected lane issues tcgen05.mma / commit
+//   warp 18     TMA producer: item tile (128 items x P_X*d fp16, SWIZZLE_128B boxes) + the tile's GI rows,
+//               double-buffered through full/empty mbarriers.  (warp 19 idle: setmaxnreg needs whole warpgroups.)
 // TMEM lanes = the 128 items of the tile; one epilogue thread owns one (query, item) pair, so every
 // reduction over the L logits is thread-local (no shuffles).  Per query and slot:
 //   G1 (SS): LOG[128 x L]   = X_tile (smem, K = 2d per item-group pair) . Qimg^T   (block-diagonal zero-padded
@@ -22,7 +23,8 @@
 //            "ones" K-block that folds the bias b1 into G2
 //   G2 (TS): HID[128 x 128] = [A2 | 1] . [0.5 W1 | 0.5 b1]^T
 //   E2     : u = HID; h = u + u tanh(u) in packed half2 (tanh.approx.f16x2) -> A3 (TMEM) + ones block
-//   G3     : GATE[128 x L]  = GI_tile (smem, SS) . diag(0.5 gq)  +  [A3 | 1] (TS) . [0.5 W2 | 0.5 b2]^T
+//   G3     : GATE[128 x L]  = GI_tile (smem, SS) . diag(0.5 gq)  +  [A3 | 1] (TS) . [0.5 W2 | 0.5 b2]^T, issued in two
+//            parts so that it starts while E2 converts the second half of the hidden units
 //   E3     : u = GATE (= half the gate pre-activation); w = u + u tanh(u); p = 2^(w log2 e) (no max
 //            subtraction: w >= -0.28 and fp32 holds e^w for w < 88; an overflow yields NaN and the
 //            caller's safety check falls back); score = sum p*l / sum p.
@@ -407,11 +409,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
         for (int j2 = 0; j2 < 8; ++j2) {
           const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
-#ifdef MOL_ABLATE_E2
-          hk[j2] = fma_f16x2(u2, u2, u2);
-#else
           hk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
-#endif
         }
         tmem_st_x8(base + col, hk);
       };
@@ -556,11 +554,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             u.y = fminf(u.y, kGateClamp);
           }
           const float2 a = __fmul2_rn(u, l2e2);
-#ifdef MOL_ABLATE_E3
-          const float2 t = u;
-#else
           const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
-#endif
           const float2 x = __ffma2_rn(a, t, a);  // w * log2(e), in [-0.41, 116]
           float2 e;
           if ((j2 & 3) < kEx2EmuOf4) {
@@ -575,11 +569,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             e.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(m.x) << 23));
             e.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(m.y) << 23));
           } else {
-#ifdef MOL_ABLATE_E3
-            e = x;
-#else
             e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-#endif
           }
           den[j2 & 3] = __fadd2_rn(den[j2 & 3], e);
           num[j2 & 3] = __ffma2_rn(e, __half22float2(*reinterpret_cast<const __half2*>(&lgc[j2])), num[j2 & 3]);

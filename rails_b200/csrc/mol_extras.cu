@@ -1,0 +1,187 @@
+// Callers / siblings of the MoL top-k path.
+//
+//  * select_valid_kernel — the seen-item masking + back-fill of
+//      indexing/candidate_index.py:155-178 (CandidateIndex.get_top_k_outputs) on the GPU, no host sync:
+//      from the over-fetched, score-sorted (B, k') list keep, per row, the first k ids that are not in the row's
+//      invalid list; rows with fewer than k valid entries are back-filled with their first invalid entries; the
+//      output keeps the original rank order of the chosen positions.
+//  * MIPS brute force — rails/indexing/mips_top_k.py:74-81: all_logits = q . items^T (fp32), top-k, id gather.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace mol {
+
+constexpr int SV_THREADS = 256;
+
+__global__ void __launch_bounds__(SV_THREADS)
+select_valid_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids,
+                    const int64_t* __restrict__ invalid, int kp, int n0, int k, float* __restrict__ out_scores,
+                    int64_t* __restrict__ out_ids) {
+  extern __shared__ int64_t sv_smem[];
+  int64_t* inv = sv_smem;                                   // n0
+  unsigned char* seen = reinterpret_cast<unsigned char*>(inv + n0);  // kp
+  __shared__ int part[SV_THREADS];
+  __shared__ int totals[2];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int64_t* row_ids = ids + (int64_t)b * kp;
+  for (int i = tid; i < n0; i += SV_THREADS) inv[i] = invalid[(int64_t)b * n0 + i];
+  __syncthreads();
+  for (int j = tid; j < kp; j += SV_THREADS) {
+    const int64_t id = row_ids[j];
+    unsigned char s = 0;
+    for (int i = 0; i < n0; ++i) s |= (inv[i] == id);
+    seen[j] = s;
+  }
+  __syncthreads();
+  // contiguous chunk per thread; two block scans (valid entries, then the complement of the kept ones)
+  const int per = (kp + SV_THREADS - 1) / SV_THREADS;
+  const int lo = tid * per, hi = min(kp, lo + per);
+  auto block_exclusive = [&](int mine, int slot) -> int {
+    part[tid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int t = 0; t < SV_THREADS; ++t) {
+        int v = part[t];
+        part[t] = run;
+        run += v;
+      }
+      totals[slot] = run;
+    }
+    __syncthreads();
+    int r = part[tid];
+    __syncthreads();
+    return r;
+  };
+  int n_valid = 0;
+  for (int j = lo; j < hi; ++j) n_valid += !seen[j];
+  const int valid_before = block_exclusive(n_valid, 0);
+  const int total_valid = totals[0];
+  const int gap = k - min(total_valid, k);  // rows with < k valid entries are back-filled
+  // kept-valid flag: valid and among the first k valid;  "invalid" := everything else (candidate_index.py:163)
+  int n_inv = 0, run = valid_before;
+  for (int j = lo; j < hi; ++j) {
+    bool keep = false;
+    if (!seen[j]) {
+      ++run;
+      keep = run <= k;
+    }
+    n_inv += !keep;
+  }
+  const int inv_before = block_exclusive(n_inv, 1);
+  int out_before;
+  {
+    // selected = kept-valid or (invalid and among the first `gap` invalid); count selected before this chunk
+    int sel = 0, rv = valid_before, ri = inv_before;
+    for (int j = lo; j < hi; ++j) {
+      bool keep = false;
+      if (!seen[j]) {
+        ++rv;
+        keep = rv <= k;
+      }
+      if (!keep) {
+        ++ri;
+        keep = ri <= gap;
+      }
+      sel += keep;
+    }
+    out_before = block_exclusive(sel, 0);
+  }
+  int rv = valid_before, ri = inv_before, o = out_before;
+  for (int j = lo; j < hi; ++j) {
+    bool keep = false;
+    if (!seen[j]) {
+      ++rv;
+      keep = rv <= k;
+    }
+    if (!keep) {
+      ++ri;
+      keep = ri <= gap;
+    }
+    if (keep && o < k) {
+      out_scores[(int64_t)b * k + o] = scores[(int64_t)b * kp + j];
+      out_ids[(int64_t)b * k + o] = row_ids[j];
+      ++o;
+    }
+  }
+}
+
+}  // namespace mol
+
+using namespace mol;
+
+extern "C" {
+
+int mol_select_valid(const float* scores, const int64_t* ids, const int64_t* invalid_ids, int32_t B,
+                     int32_t k_prime, int32_t n_invalid, int32_t k, float* out_scores, int64_t* out_ids,
+                     mol_stream_t stream) {
+  MOL_CHECK_ARG(B >= 0 && k >= 1 && k_prime >= k && n_invalid >= 0, "bad arguments (need k' >= k >= 1)");
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(scores && ids && out_scores && out_ids && (n_invalid == 0 || invalid_ids), "NULL buffer");
+  const size_t smem = (size_t)n_invalid * sizeof(int64_t) + (size_t)k_prime + 16;
+  MOL_CHECK_ARG(smem <= 200 * 1024, "k' + invalid list too large for one block (%zu bytes)", smem);
+  if (smem > 48 * 1024)
+    MOL_CUDA(cudaFuncSetAttribute(select_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  select_valid_kernel<<<B, SV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      scores, ids, invalid_ids, k_prime, n_invalid, k, out_scores, out_ids);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
+int mol_mips_workspace_bytes(int64_t num_items, int32_t B, int32_t k, size_t* bytes) {
+  MOL_CHECK_ARG(bytes && num_items >= 0 && B >= 0 && k >= 1, "bad arguments");
+  const int64_t n = num_items > 0 ? num_items : 1;
+  int64_t rows = (int64_t)(2ull << 30) / (int64_t)(sizeof(float) * (size_t)n);
+  if (rows < 1) rows = 1;
+  if (rows > B) rows = B > 0 ? B : 1;
+  size_t topk;
+  MOL_TRY(mol_topk_workspace_bytes(num_items, (int32_t)rows, k, &topk));
+  *bytes = align_up((size_t)rows * (size_t)n * sizeof(float), 256) + topk + 512;
+  return MOL_OK;
+}
+
+// scores[b, x] = <queries[b], items[x]> (fp32); out (B, N)
+int mol_dot_scores(const float* items, const float* queries, int64_t num_items, int32_t D, int32_t B,
+                   float* out_scores, mol_stream_t stream) {
+  MOL_CHECK_ARG(num_items >= 0 && D >= 1 && B >= 0, "bad arguments");
+  if (B == 0 || num_items == 0) return MOL_OK;
+  MOL_CHECK_ARG(items && queries && out_scores, "NULL buffer");
+  // C[M = B, N = items] = A[B, D] . W^T with W = items (n-major, k contiguous)
+  return launch_linear(queries, items, nullptr, out_scores, B, (int)num_items, D, D, 1, ACT_NONE,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int mol_mips_search(const float* items, const int64_t* item_ids, const float* queries, int64_t num_items,
+                    int32_t D, int32_t B, int32_t k, float* out_scores, int64_t* out_ids, void* workspace,
+                    size_t workspace_bytes, mol_stream_t stream) {
+  MOL_CHECK_ARG(num_items >= 0 && D >= 1 && B >= 0 && k >= 1 && k <= MOL_MAX_K, "bad arguments");
+  MOL_CHECK_ARG(num_items < (1ll << 31) - 256, "num_items must fit int32");
+  if (k > num_items) {
+    set_error("selected index k out of range (k=%d > %lld items)", k, (long long)num_items);
+    return MOL_ERR_RANGE;
+  }
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(items && queries && out_scores && out_ids && workspace, "NULL buffer");
+  size_t need;
+  MOL_TRY(mol_mips_workspace_bytes(num_items, B, k, &need));
+  if (workspace_bytes < need) {
+    set_error("mips workspace too small: need %zu, got %zu", need, workspace_bytes);
+    return MOL_ERR_WORKSPACE;
+  }
+  int64_t rows = (int64_t)(2ull << 30) / (int64_t)(sizeof(float) * (size_t)num_items);
+  if (rows < 1) rows = 1;
+  if (rows > B) rows = B;
+  float* mat = static_cast<float*>(workspace);
+  char* tk = static_cast<char*>(workspace) + align_up((size_t)rows * (size_t)num_items * sizeof(float), 256);
+  const size_t tk_bytes = workspace_bytes - (size_t)(tk - static_cast<char*>(workspace));
+  for (int b0 = 0; b0 < B; b0 += (int)rows) {
+    const int nb = (B - b0 < rows) ? (B - b0) : (int)rows;
+    MOL_TRY(mol_dot_scores(items, queries + (size_t)b0 * D, num_items, D, nb, mat, stream));
+    MOL_TRY(mol_topk(mat, num_items, num_items, nb, k, item_ids, out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k,
+                     tk, tk_bytes, stream));
+  }
+  return MOL_OK;
+}
+
+}  // extern "C"

@@ -268,6 +268,84 @@ def test_coarse_pass_uneven_query_split_and_many_ctas():
         assert (a - e).abs().max().item() < 0.08
 
 
+# ------------------------------------------------------------------------------- callers / siblings
+def _next_golden(name):
+    import os
+
+    import numpy as np
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    return {k_: (int(z[k_]) if k_ == "k" else torch.from_numpy(z[k_])) for k_ in z.files}
+
+
+@pytest.mark.parametrize("name", ["next_mask_basic", "next_mask_short_rows", "next_mask_wide"])
+def test_mips_and_candidate_index_match_reference(name):
+    from rails_b200.indexing.candidate_index import CandidateIndex
+    from rails_b200.indexing.mips_top_k import MIPSBruteForceTopK
+
+    g = _next_golden(name)
+    items, ids, q = g["items"].to(DEV), g["ids"].to(DEV), g["queries"].to(DEV)
+    top = MIPSBruteForceTopK(items.unsqueeze(0), ids.unsqueeze(0))
+    kp = g["ref_prime_ids"].size(1)
+    s, i = top(q, k=kp)
+    assert torch.equal(i.cpu(), g["ref_prime_ids"])                      # MIPS top-k' ids bit-exact
+    assert (s.cpu() - g["ref_prime_scores"]).abs().max().item() < 1e-5
+    index = CandidateIndex(ids=ids.unsqueeze(0), embeddings=items.unsqueeze(0))
+    out_ids, out_scores, emb = index.get_top_k_outputs(
+        query_embeddings=q, k=g["k"], aux_payloads={}, top_k_module=top, invalid_ids=g["invalid_ids"].to(DEV)
+    )
+    assert emb is None
+    assert torch.equal(out_ids.cpu(), g["ref_ids"])                      # masking + back-fill bit-exact
+    assert (out_scores.cpu() - g["ref_scores"]).abs().max().item() < 1e-5
+
+
+def test_select_valid_matches_oracle_random():
+    from oracle import next_oracle as NO
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7)
+    for B, kp, n0, k in [(3, 50, 0, 50), (8, 400, 211, 200), (2, 2711, 211, 2500), (5, 64, 70, 10)]:
+        ids = torch.stack([torch.randperm(5000, generator=g)[:kp] + 1 for _ in range(B)])
+        scores = torch.sort(torch.randn(B, kp, generator=g), dim=1, descending=True).values
+        inv = torch.randint(0, 5001, (B, max(n0, 1)), generator=g)
+        if n0 > 0:
+            inv[:, : min(n0, kp) // 2] = ids[:, : min(n0, kp) // 2]
+        else:
+            inv = inv[:, :0]
+        rs, ri = NO.select_valid(scores, ids, inv, k) if n0 > 0 else (scores[:, :k], ids[:, :k])
+        ds, di, dinv = scores.to(DEV), ids.to(DEV), inv.to(DEV).contiguous()
+        out_s = torch.empty(B, k, device=DEV)
+        out_i = torch.empty(B, k, dtype=torch.int64, device=DEV)
+        import ctypes
+
+        _lib.check(lib.mol_select_valid(
+            ctypes.c_void_p(ds.data_ptr()), ctypes.c_void_p(di.data_ptr()), ctypes.c_void_p(dinv.data_ptr() if n0 else 0),
+            B, kp, n0, k, ctypes.c_void_p(out_s.data_ptr()), ctypes.c_void_p(out_i.data_ptr()),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        assert torch.equal(out_i.cpu(), ri) and torch.equal(out_s.cpu(), rs)
+
+
+def test_mol_candidate_index_with_seen_items_matches_oracle():
+    """The full eval-side call: CandidateIndex.get_top_k_outputs over MoLBruteForceTopK with per-row seen ids."""
+    from oracle import next_oracle as NO
+    from rails_b200.indexing.candidate_index import CandidateIndex
+
+    cfg = CFG_8x8x32
+    N, B, k, n0 = 5000, 6, 20, 16
+    mol, _ = build_module(cfg, None, DEV, seed=8)
+    items, ids, q, _ = synthetic_inputs(cfg, N, B, 8, DEV)
+    top = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0))
+    sd = {k_: v.detach().cpu() for k_, v in mol.state_dict().items()}
+    ps, pi, all_scores = O.brute_force_top_k(cfg, sd, q.cpu(), items.cpu(), ids.cpu(), k + n0)
+    inv = pi[:, ::2][:, :n0].contiguous()  # every other of the row's best items has been "seen"
+    rs, ri = NO.select_valid(ps, pi, inv, k)
+    index = CandidateIndex(ids=ids.unsqueeze(0), embeddings=items.unsqueeze(0))
+    out_ids, out_scores, _ = index.get_top_k_outputs(q, k, {}, top, inv.to(DEV))
+    assert torch.equal(out_ids.cpu(), ri)
+    assert (out_scores.cpu() - rs).abs().max().item() < SCORE_TOL
+
+
 # ------------------------------------------------------------------------------- multi-GPU (needs >= 2 devices)
 def _nccl_worker(rank, world, port, out):
     import os

@@ -1,0 +1,43 @@
+"""Pins oracle/next_oracle.py (seen-item masking, MIPS top-k) against outputs of the UNMODIFIED reference
+(tests/golden/next_*.npz, written by oracle/gen_golden_next.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import next_oracle as NO
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "next_*.npz")))
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: (int(z[k]) if k == "k" else torch.from_numpy(z[k])) for k in z.files}
+
+
+def test_fixtures_present():
+    assert {"next_mask_basic", "next_mask_short_rows", "next_mask_wide"} <= set(NAMES)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_mips_oracle_matches_reference(name):
+    g = load(name)
+    kp = g["ref_prime_ids"].size(1)
+    s, i, _ = NO.mips_top_k(g["queries"], g["items"], g["ids"], kp)
+    assert torch.equal(i, g["ref_prime_ids"]) and torch.allclose(s, g["ref_prime_scores"], atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_select_valid_oracle_matches_reference(name):
+    g = load(name)
+    s, i = NO.select_valid(g["ref_prime_scores"], g["ref_prime_ids"], g["invalid_ids"], g["k"])
+    assert torch.equal(i, g["ref_ids"]) and torch.equal(s, g["ref_scores"])
+
+
+def test_short_rows_fixture_really_backfills():
+    g = load("next_mask_short_rows")
+    seen = (g["ref_prime_ids"].unsqueeze(2) == g["invalid_ids"].unsqueeze(1)).any(2)
+    assert bool(((~seen).sum(1) < g["k"]).any()), "fixture must contain rows with fewer than k valid candidates"
