@@ -8,7 +8,7 @@
 // (B, N, H) hidden activations and (B, N, L) gates never leave the SM.  Its output only RANKS
 // candidates; final scores come from the fp32 rescoring pass (mol_exact.cu).
 //
-// Mapping (one persistent CTA per SM, 640 threads = 5 warpgroups; setmaxnreg splits the register file 160/56/48):
+// Mapping (one persistent CTA per SM, 640 threads = 5 warpgroups; setmaxnreg splits the register file 168/48/40):
 //   per TMEM slot s (2 slots, 256 columns each; slot 0 takes the even queries of a tile's range, slot 1 the odd ones):
 //     warps 8s+0..3   E1/E3 warpgroup: logits -> fp16 operand (E1), gate -> softmax-weighted score -> output (E3)
 //     warps 8s+4..7   E2 warpgroup   : hidden pre-activations -> silu -> fp16 operand
@@ -49,7 +49,7 @@ constexpr int kCtlWarp0 = kEpiThreads / 32;    // control warpgroup: issuer slot
 constexpr int kThreads = kEpiThreads + 4 * 32;
 // setmaxnreg split of the 64K-register file (the kernel is compiled for 640 threads -> 96 registers at launch)
 // (setmaxnreg only redistributes the CTA's own launch allocation: 640 x 96 = 61440 registers)
-constexpr int kE13Regs = 160, kE2Regs = 56, kCtlRegs = 48;
+constexpr int kE13Regs = 168, kE2Regs = 48, kCtlRegs = 40;
 static_assert(256 * kE13Regs + 256 * kE2Regs + 128 * kCtlRegs <= kThreads * 96, "register pool over-committed");
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kK3 = kH + 16;    // K of the gate GEMM's TS part: hidden units + the ones block
@@ -503,21 +503,25 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tc_fence_after();
       if (warp == 0) TR(0, 1, cnt);
       {
-        uint32_t la[32], lb[32];
-        tmem_ld_x32(base + kColLog, la);
-        if constexpr (L == 64) tmem_ld_x32(base + kColLog + 32, lb);
+        // LOG in chunks of 16 columns, two chunks in flight (keeps the register peak at 2 x 16 + the packed logits)
+        uint32_t la[16], lb[16];
+        tmem_ld_x16(base + kColLog, la);
+        tmem_ld_x16(base + kColLog + 16, lb);
         // G1 of this query is complete: its image buffer is free for the next query
         if (have_n) store_image();
         fence_proxy_async_smem();
-        tmem_ld_wait_bind32(la);
 #pragma unroll
-        for (int j2 = 0; j2 < 16; ++j2)
-          pk[j2] = pack_f16x2(__uint_as_float(la[2 * j2]), __uint_as_float(la[2 * j2 + 1]));
-        if constexpr (L == 64) {
-          tmem_ld_wait_bind32(lb);
+        for (int c = 0; c < L / 16; c += 2) {
+          tmem_ld_wait_bind16(la);
+          tmem_ld_wait_bind16(lb);
 #pragma unroll
-          for (int j2 = 0; j2 < 16; ++j2)
-            pk[16 + j2] = pack_f16x2(__uint_as_float(lb[2 * j2]), __uint_as_float(lb[2 * j2 + 1]));
+          for (int j2 = 0; j2 < 8; ++j2)
+            pk[8 * c + j2] = pack_f16x2(__uint_as_float(la[2 * j2]), __uint_as_float(la[2 * j2 + 1]));
+          if (c + 2 < L / 16) tmem_ld_x16(base + kColLog + 16 * (c + 2), la);
+#pragma unroll
+          for (int j2 = 0; j2 < 8; ++j2)
+            pk[8 * c + 8 + j2] = pack_f16x2(__uint_as_float(lb[2 * j2]), __uint_as_float(lb[2 * j2 + 1]));
+          if (c + 3 < L / 16) tmem_ld_x16(base + kColLog + 16 * (c + 3), lb);
         }
       }
       if constexpr (L == 64) {
@@ -544,10 +548,10 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       float2 num[4], den[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) num[i] = den[i] = make_float2(0.f, 0.f);
-      uint32_t va[32], vb[32];
+      uint32_t v0[16], v1[16], v2[16];
       auto gate = [&](const uint32_t* v, const uint32_t* lgc) __attribute__((always_inline)) {
 #pragma unroll
-        for (int j2 = 0; j2 < 16; ++j2) {
+        for (int j2 = 0; j2 < 8; ++j2) {
           float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
           if (kEx2EmuOf4 > 0) {  // the exponent-field trick has no inf: keep e^w finite (w = silu(2u) <= 80)
             u.x = fminf(u.x, kGateClamp);
@@ -575,20 +579,36 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           num[j2 & 3] = __ffma2_rn(e, __half22float2(*reinterpret_cast<const __half2*>(&lgc[j2])), num[j2 & 3]);
         }
       };
-      tmem_ld_x32(base + kColGate, va);
-      if constexpr (L == 64) tmem_ld_x32(base + kColGate + 32, vb);
+      // GATE in chunks of 16 columns through three buffers; GATE is released once the last chunk has landed
+      tmem_ld_x16(base + kColGate, v0);
+      tmem_ld_x16(base + kColGate + 16, v1);
       if (stage_diag) {
         if (r < L) *sDw = gqv;  // G3 of this query is complete (gate_full): the diag buffer is free
         fence_proxy_async_smem();
       }
-      tmem_ld_wait_bind32(va);
-      if constexpr (L == 64) tmem_ld_wait_bind32(vb);
-      if (stage_diag) {
-        tc_fence_before();
-        mbar_arrive(&bars->gate_free[wg]);
+      tmem_ld_wait_bind16(v0);
+      tmem_ld_wait_bind16(v1);
+      if constexpr (L == 64) {
+        tmem_ld_x16(base + kColGate + 32, v2);
+        gate(v0, pk);
+        tmem_ld_x16(base + kColGate + 48, v0);
+        gate(v1, pk + 8);
+        tmem_ld_wait_bind16(v2);
+        tmem_ld_wait_bind16(v0);
+        if (stage_diag) {
+          tc_fence_before();
+          mbar_arrive(&bars->gate_free[wg]);
+        }
+        gate(v2, pk + 16);
+        gate(v0, pk + 24);
+      } else {
+        if (stage_diag) {
+          tc_fence_before();
+          mbar_arrive(&bars->gate_free[wg]);
+        }
+        gate(v0, pk);
+        gate(v1, pk + 8);
       }
-      gate(va, pk);
-      if constexpr (L == 64) gate(vb, pk + 16);
       const float2 n2 = __fadd2_rn(__fadd2_rn(num[0], num[1]), __fadd2_rn(num[2], num[3]));
       const float2 d2 = __fadd2_rn(__fadd2_rn(den[0], den[1]), __fadd2_rn(den[2], den[3]));
       const float score = __fdividef(n2.x + n2.y, d2.x + d2.y);
