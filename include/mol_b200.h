@@ -183,6 +183,17 @@ int mol_mips_search(const float* items, const int64_t* item_ids, const float* qu
 int mol_dot_scores(const float* items, const float* queries, int64_t num_items, int32_t D, int32_t B,
                    float* out_scores, mol_stream_t stream);
 
+/* MoLAvgTopK (rails/indexing/mol_top_k.py:296-429): dot-product prefilter on the
+ * group-averaged sub-embeddings (fp32 here; the reference keeps them in bf16), top avg_top_k positions, exact fp32 MoL
+ * on those, final top-k.  avg_items (N, d) = mean over P_X of the index's X_sub, filled by mol_index_avg_embeddings. */
+int mol_index_avg_embeddings(const mol_shape_t* shape, const mol_index_t* index, float* out_avg, mol_stream_t stream);
+int mol_search_avg_workspace_bytes(const mol_shape_t* shape, int64_t num_items, int32_t B, int32_t k,
+                                   int32_t avg_top_k, size_t* bytes);
+int mol_search_avg(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index, const float* avg_items,
+                   const float* queries, const int64_t* user_ids, int32_t B, int32_t k, int32_t avg_top_k,
+                   float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                   mol_stream_t stream);
+
 /* Optional CUDA-event timing of the dominant scoring kernel (the tcgen05 coarse pass, or the fp32
  * kernel in MOL_MODE_EXACT) on the stream it is launched on: enable, run searches, collect the summed
  * device time and the number of timed launches (collect synchronises on the recorded events). */

@@ -50,7 +50,44 @@ def case(name, N, D, B, k, n0, seed, force_short_rows=False):
     print(name, "k'", kp, "->", tuple(out_ids.shape))
 
 
+def avg_case(name, cfg, N, B, k, avg_top_k, seed):
+    """Reference MoLAvgTopK (rails/indexing/mol_top_k.py:296-429).  Stored twice: with the reference's default bf16
+    component embeddings, and with them replaced by fp32 (what rails_b200 computes)."""
+    import json
+
+    from oracle.reference_loader import build_reference_mol
+    from rails.indexing.mol_top_k import MoLAvgTopK
+    from tests.helpers import synthetic_inputs
+
+    torch.manual_seed(seed)
+    mol = build_reference_mol(cfg).eval()
+    items, ids, q, uid = synthetic_inputs(cfg, N, B, seed)
+    kw = {} if uid is None else {"user_ids": uid}
+    with torch.inference_mode():
+        top = MoLAvgTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), avg_top_k)
+        s_bf16, i_bf16 = top(q, k=k, **kw)
+        comp, _ = mol.get_item_component_embeddings(items, decoupled_inference=True)
+        top._mol_item_embeddings = comp.float()
+        top._avg_mol_item_embeddings_t = (comp.float().sum(1) / comp.size(1)).transpose(0, 1)
+        s_f32, i_f32 = top(q, k=k, **kw)
+    out = {f"sd::{k_}": v.detach().numpy() for k_, v in mol.state_dict().items()}
+    out.update(
+        cfg=np.frombuffer(json.dumps(cfg.to_json()).encode(), dtype=np.uint8), items=items.numpy(), item_ids=ids.numpy(),
+        queries=q.numpy(), k=np.int64(k), avg_top_k=np.int64(avg_top_k),
+        ref_scores_f32=s_f32.numpy(), ref_ids_f32=i_f32.numpy(), ref_scores_bf16=s_bf16.float().numpy(), ref_ids_bf16=i_bf16.numpy(),
+    )
+    if uid is not None:
+        out["user_ids"] = uid.numpy()
+    np.savez_compressed(os.path.join(OUT, f"next_{name}.npz"), **out)
+    print(name, tuple(i_f32.shape), "bf16-vs-fp32 prefilter id overlap:",
+          float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(i_f32, i_bf16)])))
+
+
 if __name__ == "__main__":
+    from tests.helpers import CFG_8x8x32, CFG_8x4x64
+
+    avg_case("avg_8x8x32", CFG_8x8x32, N=4000, B=5, k=20, avg_top_k=200, seed=11)
+    avg_case("avg_8x4x64_uid", CFG_8x4x64, N=1500, B=4, k=10, avg_top_k=64, seed=12)
     case("mask_basic", N=500, D=16, B=6, k=10, n0=12, seed=1)
     case("mask_short_rows", N=40, D=8, B=5, k=30, n0=25, seed=2, force_short_rows=True)  # k' clamps to N, rows back-fill
     case("mask_wide", N=3000, D=32, B=4, k=100, n0=211, seed=3)

@@ -35,3 +35,24 @@ def mips_top_k(
     all_logits = torch.mm(query_embeddings, item_embeddings.t())
     s, i = torch.topk(all_logits, dim=1, k=k, sorted=True, largest=True)
     return s, item_ids.reshape(-1)[i], all_logits
+
+
+def mol_avg_top_k(cfg, sd, query_embeddings, item_embeddings, item_ids, k: int, avg_top_k: int, user_ids=None):
+    """MoLAvgTopK.forward with fp32 component embeddings (mol_top_k.py:331-385).
+    Returns (top scores (B, k), top ids (B, k), prefilter positions (B, avg_top_k))."""
+    from oracle import mol_oracle as O
+
+    qs = O.query_sub_embeddings(cfg, sd, query_embeddings, user_ids)  # (B, P_Q, d)
+    xs = O.item_sub_embeddings(cfg, sd, item_embeddings)  # (N, P_X, d)
+    avg_items = xs.sum(1) / xs.size(1)  # :322-324
+    avg_sim = torch.mm(qs.sum(1), avg_items.t())  # :352-356
+    _, pos = torch.topk(avg_sim, k=avg_top_k, dim=1)  # :357-360
+    scores = torch.stack(
+        [
+            O.similarity(cfg, sd, query_embeddings[b : b + 1], item_embeddings[pos[b]],
+                         None if user_ids is None else user_ids[b : b + 1])[0]
+            for b in range(query_embeddings.size(0))
+        ]
+    )  # :368-373 (B'==B branch == per-query candidate lists)
+    s, j = torch.topk(scores, k=min(k, avg_top_k), dim=1, largest=True, sorted=True)  # :374-380
+    return s, item_ids.reshape(-1)[torch.gather(pos, 1, j)], pos

@@ -602,6 +602,142 @@ int mol_score_all_coarse(const mol_shape_t* shape, const mol_weights_t* w, const
   return coarse_scores(*shape, *index, ws.coarse, ws.qsub, ws.gq, B, out_scores, st);
 }
 
+}  // extern "C"
+namespace mol {
+// ---- MoLAvgTopK (rails/indexing/mol_top_k.py:296-429): dot-product prefilter on group-averaged embeddings, then
+// exact MoL on the avg_top_k survivors -------------------------------------------
+__global__ void avg_groups_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int groups,
+                                  int d, float scale) {  // out[r, :] = scale * sum_g in[r, g, :]
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * d) return;
+  const int64_t r = i / d;
+  const int c = (int)(i % d);
+  float s = 0.f;
+  for (int g = 0; g < groups; ++g) s += in[(r * groups + g) * d + c];
+  out[i] = s * scale;
+}
+
+struct AvgWs {
+  float *pre, *h, *proj, *hq, *qsub, *gq, *w1t, *w2t, *qsum, *scores, *seg_scores, *exact;
+  int32_t *seg_idx, *cand_idx;
+  float* cand_scores;
+  int rows;
+  size_t total;
+};
+
+static int plan_avg(const mol_shape_t& s, int64_t N, int B, int k, int avg_top_k, void* base, size_t cap, AvgWs* ws) {
+  Dims D = dims_of(s);
+  Arena a(base, cap);
+  ws->pre = a.take<float>((size_t)B * 2 * D.Hq);
+  ws->h = a.take<float>((size_t)B * D.Hq);
+  ws->proj = a.take<float>((size_t)B * D.Pq_proj * D.d);
+  ws->hq = a.take<float>((size_t)B * D.Hgq);
+  ws->qsub = a.take<float>((size_t)B * D.Pq * D.d);
+  ws->gq = a.take<float>((size_t)B * D.L);
+  ws->w1t = a.take<float>((size_t)D.L * D.H);
+  ws->w2t = a.take<float>((size_t)D.L * D.H);
+  ws->qsum = a.take<float>((size_t)B * D.d);
+  const int64_t n = N > 0 ? N : 1;
+  int64_t rows = (int64_t)(2ull << 30) / (int64_t)(sizeof(float) * (size_t)n);
+  if (rows < 1) rows = 1;
+  if (rows > B) rows = B > 0 ? B : 1;
+  ws->rows = (int)rows;
+  ws->scores = a.take<float>((size_t)rows * (size_t)n);
+  const size_t seg = (size_t)(rows + 2 * 148 + 1) * (size_t)avg_top_k;
+  ws->seg_scores = a.take<float>(seg);
+  ws->seg_idx = a.take<int32_t>(seg);
+  ws->cand_scores = a.take<float>((size_t)B * avg_top_k);
+  ws->cand_idx = a.take<int32_t>((size_t)B * avg_top_k);
+  ws->exact = a.take<float>((size_t)B * avg_top_k);
+  (void)k;
+  ws->total = align_up(a.off, 256);
+  if (base != nullptr && a.off > cap) {
+    set_error("workspace too small: need %zu bytes, got %zu", ws->total, cap);
+    return MOL_ERR_WORKSPACE;
+  }
+  return MOL_OK;
+}
+
+}  // namespace mol
+using namespace mol;
+extern "C" {
+
+int mol_index_avg_embeddings(const mol_shape_t* shape, const mol_index_t* index, float* out_avg, mol_stream_t stream) {
+  MOL_TRY(check_shape(shape));
+  MOL_CHECK_ARG(index && index->xsub_f32 && out_avg, "index not laid out / NULL output");
+  Dims D = dims_of(*shape);
+  const int64_t total = index->num_items * D.d;
+  if (total == 0) return MOL_OK;
+  avg_groups_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      index->xsub_f32, out_avg, index->num_items, D.Px, D.d, 1.0f / D.Px);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
+int mol_search_avg_workspace_bytes(const mol_shape_t* shape, int64_t num_items, int32_t B, int32_t k,
+                                   int32_t avg_top_k, size_t* bytes) {
+  MOL_TRY(check_shape(shape));
+  MOL_CHECK_ARG(bytes && B >= 0 && k >= 1 && avg_top_k >= 1 && num_items >= 0, "bad arguments");
+  AvgWs ws;
+  MOL_TRY(plan_avg(*shape, num_items, B > 0 ? B : 1, k, avg_top_k, nullptr, 0, &ws));
+  *bytes = ws.total + 256;
+  return MOL_OK;
+}
+
+int mol_search_avg(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index, const float* avg_items,
+                   const float* queries, const int64_t* user_ids, int32_t B, int32_t k, int32_t avg_top_k,
+                   float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                   mol_stream_t stream) {
+  MOL_TRY(check_shape(shape));
+  MOL_TRY(check_weights(shape, w));
+  MOL_CHECK_ARG(index && index->xsub_f32 && index->gi_f32 && avg_items, "index not laid out / avg embeddings missing");
+  MOL_CHECK_ARG(B >= 0 && k >= 1 && avg_top_k >= 1 && avg_top_k <= MOL_MAX_K, "bad arguments");
+  MOL_CHECK_ARG(k <= avg_top_k, "avg_top_k (%d) must be larger than k (%d)", avg_top_k, k);
+  const int64_t N = index->num_items;
+  if (avg_top_k > N) {
+    set_error("selected index k out of range (avg_top_k=%d > %lld items)", avg_top_k, (long long)N);
+    return MOL_ERR_RANGE;
+  }
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(queries && out_scores && out_ids && workspace, "NULL buffer");
+  MOL_CHECK_ARG(shape->num_uid_tables == 0 || user_ids, "user_ids required when uid embeddings are configured");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Dims D = dims_of(*shape);
+  AvgWs ws;
+  MOL_TRY(plan_avg(*shape, N, B, k, avg_top_k, workspace, workspace_bytes, &ws));
+  MOL_TRY(run_query_prologue(*shape, *w, queries, user_ids, B, ws.pre, ws.h, ws.proj, ws.hq, ws.qsub, ws.gq, st));
+  MOL_TRY(launch_transpose(w->qi_w1, ws.w1t, D.H, D.L, st));
+  MOL_TRY(launch_transpose(w->qi_w2, ws.w2t, D.L, D.H, st));
+  {  // mol_top_k.py:352-356: mol_query_embeddings.sum(1)
+    const int64_t total = (int64_t)B * D.d;
+    avg_groups_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.qsub, ws.qsum, B, D.Pq, D.d, 1.0f);
+    MOL_LAUNCH_CHECK();
+  }
+  for (int b0 = 0; b0 < B; b0 += ws.rows) {
+    const int nb = (B - b0 < ws.rows) ? (B - b0) : ws.rows;
+    // avg_sim_values = q_sum . avg_items^T ; top avg_top_k positions per query (:352-360)
+    MOL_TRY(launch_linear(ws.qsum + (size_t)b0 * D.d, avg_items, nullptr, ws.scores, nb, (int)N, D.d, D.d, 1, ACT_NONE, st));
+    const int S = select_num_segments(N, nb, avg_top_k);
+    const float* sel = ws.scores;
+    const int32_t* pay = nullptr;
+    int64_t sn = N, sld = N;
+    if (S > 1) {
+      MOL_TRY(launch_select_segments(ws.scores, N, N, nb, S, avg_top_k, ws.seg_scores, ws.seg_idx, nullptr, st));
+      sel = ws.seg_scores;
+      pay = ws.seg_idx;
+      sn = (int64_t)S * avg_top_k;
+      sld = sn;
+    }
+    MOL_TRY(launch_select_final_i32(sel, pay, sn, sld, nb, avg_top_k, ws.cand_scores + (size_t)b0 * avg_top_k,
+                                    ws.cand_idx + (size_t)b0 * avg_top_k, nullptr, nullptr, nullptr, st));
+  }
+  // exact MoL on the survivors (:368-373), final top-k and id map (:374-385)
+  MOL_TRY(launch_exact_scores(*shape, *w, *index, ws.w1t, ws.w2t, ws.qsub, ws.gq, B, ws.cand_idx, avg_top_k, avg_top_k,
+                              ws.exact, nullptr, st));
+  return launch_select_final_i32(ws.exact, ws.cand_idx, avg_top_k, avg_top_k, B, k, out_scores, nullptr, out_ids,
+                                 index->item_ids, nullptr, st);
+}
+
 int mol_query_prologue(const mol_shape_t* shape, const mol_weights_t* w, const float* queries,
                        const int64_t* user_ids, int32_t B, float* out_qsub, float* out_gq,
                        void* workspace, size_t workspace_bytes, mol_stream_t stream) {

@@ -328,3 +328,48 @@ def topk(scores: torch.Tensor, k: int, id_map: Optional[torch.Tensor] = None) ->
             )
         )
     return out_s, out_i
+
+
+def search_avg(
+    weights: PackedWeights,
+    index: IndexHandle,
+    avg_items: torch.Tensor,
+    workspace: Workspace,
+    queries: torch.Tensor,
+    user_ids: Optional[torch.Tensor],
+    k: int,
+    avg_top_k: int,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """mol_search_avg: MoLAvgTopK.forward on the GPU.  Returns (scores (B,k) fp32, ids (B,k) int64)."""
+    lib = _lib.load()
+    _require_cuda(queries, "query_embeddings")
+    dev = index.device
+    q = queries.detach().to(device=dev, dtype=torch.float32).contiguous()
+    B = int(q.size(0))
+    uid = None
+    if weights.shape.num_uid_tables > 0:
+        if user_ids is None:
+            raise KeyError("user_ids")
+        uid = user_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
+    out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+    nbytes = c_size_t()
+    _lib.check(lib.mol_search_avg_workspace_bytes(byref(weights.shape), index.N, B, k, avg_top_k, byref(nbytes)))
+    ws = workspace.get(nbytes.value)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.mol_search_avg(
+                byref(weights.shape), byref(weights.struct), byref(index.struct), _ptr(avg_items), _ptr(q), _ptr(uid),
+                B, k, avg_top_k, _ptr(out_s), _ptr(out_i), _ptr(ws), ws.numel(), _stream_ptr(dev),
+            )
+        )
+    return out_s, out_i
+
+
+def avg_item_embeddings(weights: PackedWeights, index: IndexHandle) -> torch.Tensor:
+    """(N, d) fp32 mean over the P_X item sub-embeddings (MoLAvgTopK's prefilter operand)."""
+    lib = _lib.load()
+    out = torch.empty((index.N, weights.shape.dot_product_dimension), dtype=torch.float32, device=index.device)
+    with torch.cuda.device(index.device):
+        _lib.check(lib.mol_index_avg_embeddings(byref(weights.shape), byref(index.struct), _ptr(out), _stream_ptr(index.device)))
+    return out

@@ -114,3 +114,42 @@ class MoLBruteForceTopK(MoLTopKModule):
             kwargs.get("user_ids"), int(k), sorted, self._mode,
         )
         return scores.to(query_embeddings.dtype), ids
+
+
+class MoLAvgTopK(MoLTopKModule):
+    """Approximate MoL top-k of the reference (mol_top_k.py:296-429): a dot-product prefilter on the group-averaged
+    sub-embeddings keeps `avg_top_k` items per query, exact MoL is evaluated on those and the best k are returned.
+    Everything runs in `mol_search_avg`; the prefilter operand is kept in fp32 (the reference defaults to bf16
+    component embeddings, mol_top_k.py:37), so the candidate set can only be more faithful to the fp32 dot products.
+    SURVEY.md §8 row f3."""
+
+    def __init__(self, mol_module: MoLSimilarity, item_embeddings: torch.Tensor, item_ids: torch.Tensor, avg_top_k: int) -> None:
+        super().__init__(
+            mol_module=mol_module,
+            item_embeddings=item_embeddings,
+            item_ids=item_ids,
+            flatten_item_ids_and_embeddings=True,
+            keep_component_level_item_embeddings=False,
+        )
+        self._avg_top_k: int = int(avg_top_k)
+        self._avg_items = None
+        self._avg_key = None
+
+    def _ensure_avg(self):
+        index = self._ensure_index()
+        if self._avg_items is None or self._avg_key is not self._index:
+            self._avg_items = engine.avg_item_embeddings(self._mol_module.packed_weights(index.device), index)
+            self._avg_key = self._index
+        return index, self._avg_items
+
+    @torch.no_grad()
+    def forward(self, query_embeddings: torch.Tensor, k: int, sorted: bool = True, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        if k > self._avg_top_k:
+            raise ValueError(f"avg_top_k ({self._avg_top_k}) must be larger than k ({k})")
+        index, avg = self._ensure_avg()
+        dev = index.device
+        scores, ids = engine.search_avg(
+            self._mol_module.packed_weights(dev), index, avg, self._mol_module.workspace(dev), query_embeddings,
+            kwargs.get("user_ids"), int(k), self._avg_top_k,
+        )
+        return scores.to(query_embeddings.dtype), ids

@@ -10,7 +10,8 @@ import torch
 from oracle import next_oracle as NO
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "next_*.npz")))
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "next_mask_*.npz")))
+AVG_NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "next_avg_*.npz")))
 
 
 def load(name):
@@ -41,3 +42,33 @@ def test_short_rows_fixture_really_backfills():
     g = load("next_mask_short_rows")
     seen = (g["ref_prime_ids"].unsqueeze(2) == g["invalid_ids"].unsqueeze(1)).any(2)
     assert bool(((~seen).sum(1) < g["k"]).any()), "fixture must contain rows with fewer than k valid candidates"
+
+
+def load_avg(name):
+    import json
+
+    from oracle.mol_oracle import MoLConfig
+
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    out = {"sd": {}, "user_ids": None}
+    for key in z.files:
+        if key.startswith("sd::"):
+            out["sd"][key[4:]] = torch.from_numpy(z[key])
+        elif key == "cfg":
+            out["cfg"] = MoLConfig.from_json(json.loads(bytes(z[key]).decode()))
+        elif key in ("k", "avg_top_k"):
+            out[key] = int(z[key])
+        else:
+            out[key] = torch.from_numpy(z[key])
+    return out
+
+
+@pytest.mark.parametrize("name", AVG_NAMES)
+def test_mol_avg_oracle_matches_reference(name):
+    g = load_avg(name)
+    s, i, _ = NO.mol_avg_top_k(g["cfg"], g["sd"], g["queries"], g["items"], g["item_ids"], g["k"], g["avg_top_k"], g["user_ids"])
+    assert torch.equal(i, g["ref_ids_f32"])
+    assert (s - g["ref_scores_f32"]).abs().max().item() < 1e-5
+    # the reference's default bf16 component embeddings select (almost) the same items
+    overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / g["k"] for a, b in zip(g["ref_ids_f32"], g["ref_ids_bf16"])])
+    assert overlap >= 0.9
