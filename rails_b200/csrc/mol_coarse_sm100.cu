@@ -8,10 +8,10 @@
 // (B, N, H) hidden activations and (B, N, L) gates never leave the SM.  Its output only RANKS
 // candidates; final scores come from the fp32 rescoring pass (mol_exact.cu).
 //
-// Mapping (one persistent CTA per SM, 640 threads = 5 warpgroups; setmaxnreg splits the register file 168/48/40):
+// Mapping (one persistent CTA per SM, 640 threads = 5 warpgroups; setmaxnreg splits the register file 160/56/48):
 //   per TMEM slot s (2 slots, 256 columns each; slot 0 takes the even queries of a tile's range, slot 1 the odd ones):
-//     warps 8s+0..3   E1/E3 warpgroup: logits -> fp16 operand (E1), gate -> softmax-weighted score -> output (E3)
-//     warps 8s+4..7   E2 warpgroup   : hidden pre-activations -> silu -> fp16 operand
+//     warps 8s+0..3   E3 warpgroup   : stages query images / diag, gate -> softmax-weighted score -> output (E3)
+//     warps 8s+4..7   E1/E2 warpgroup: logits -> fp16 operand (E1), hidden pre-activations -> silu -> fp16 operand (E2)
 //   warp 16/17  MMA issuer of slot 0 / 1: the warp runs converged, one elected lane issues tcgen05.mma / commit
 //   warp 18     TMA producer: item tile (128 items x P_X*d fp16, SWIZZLE_128B boxes) + the tile's GI rows,
 //               double-buffered through full/empty mbarriers.  (warp 19 idle: setmaxnreg needs whole warpgroups.)
@@ -49,7 +49,7 @@ constexpr int kCtlWarp0 = kEpiThreads / 32;    // control warpgroup: issuer slot
 constexpr int kThreads = kEpiThreads + 4 * 32;
 // setmaxnreg split of the 64K-register file (the kernel is compiled for 640 threads -> 96 registers at launch)
 // (setmaxnreg only redistributes the CTA's own launch allocation: 640 x 96 = 61440 registers)
-constexpr int kE13Regs = 168, kE2Regs = 48, kCtlRegs = 40;
+constexpr int kE13Regs = 160, kE2Regs = 56, kCtlRegs = 48;
 static_assert(256 * kE13Regs + 256 * kE2Regs + 128 * kCtlRegs <= kThreads * 96, "register pool over-committed");
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kK3 = kH + 16;    // K of the gate GEMM's TS part: hidden units + the ones block
@@ -58,7 +58,17 @@ constexpr float kGateClamp = 40.f;  // clamp of the half gate pre-activation u (
 #ifndef MOL_EX2_EMU_OF4
 #define MOL_EX2_EMU_OF4 0  // measured on B200: 0 is fastest ("what did not work")
 #endif
-constexpr int kEx2EmuOf4 = MOL_EX2_EMU_OF4;  // of every 4 logit pairs, how many take 2^x on the FMA pipe instead of MUFU.EX2
+constexpr int kEx2EmuOf4 = MOL_EX2_EMU_OF4;
+#ifndef MOL_E2_POLY_MASK
+#define MOL_E2_POLY_MASK 0x00
+#endif
+// bit c set: chunk c (16 hidden units) of E2 takes tanh from an fp32 odd polynomial on the FMA pipe instead of MUFU.TANH
+constexpr unsigned kE2PolyMask = MOL_E2_POLY_MASK;
+// tanh(u) ~ c * Q(c^2), c = clamp(u, +-3.5), |error| <= 1.9e-3 (minimax fit, tools/fit notes in DESIGN.md)
+constexpr float kTanhC = 3.5f;
+constexpr float kT0 = 0.9905173778533936f, kT1 = -0.29184621572494507f, kT2 = 0.07649415731430054f,
+                kT3 = -0.013051184825599194f, kT4 = 0.0013143233954906464f, kT5 = -7.031815766822547e-05f,
+                kT6 = 1.5339735455199843e-06f;  // of every 4 logit pairs, how many take 2^x on the FMA pipe instead of MUFU.EX2
 
 // TMEM column map of one slot (256 columns)
 constexpr uint32_t kColLog = 0;     // LOG fp32 [0, L); A2 fp16 aliases [0, L/2) + ones [L/2, L/2 + 8)
@@ -126,7 +136,7 @@ __host__ __device__ inline uint32_t nosw_off(int r, int k, int K) {
 
 struct Bars {
   uint64_t full[2], empty[2];
-  uint64_t q0_ready[2], e1_done[2], e2a_done[2], e2_done[2], gate_free[2];
+  uint64_t q0_ready[2], e1_done[2], a2_read[2], e2a_done[2], e2_done[2], gate_free[2];
   uint64_t log_full[2], hid_full[2], gate_full[2];
   uint32_t tmem_base;
 };
@@ -210,6 +220,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_init(&bars->empty[s], 2);
       mbar_init(&bars->q0_ready[s], 128);
       mbar_init(&bars->e1_done[s], 128);
+      mbar_init(&bars->a2_read[s], 128);
       mbar_init(&bars->e2a_done[s], 128);
       mbar_init(&bars->e2_done[s], 128);
       mbar_init(&bars->gate_free[s], 128);
@@ -276,7 +287,11 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
           for (int g = 0; g < C::NG; ++g) {
 #pragma unroll
+#ifdef MOL_ABLATE_G1
+            for (int ks = 0; ks < C::K1 / 32; ++ks) {  // (timing experiment: half the K steps)
+#else
             for (int ks = 0; ks < C::K1 / 16; ++ks) {
+#endif
               const int e = g * C::K1 + ks * 16;  // first fp16 column of this K step in the item row
               const uint64_t da = make_smem_desc(sXa + (e / 64) * 16384 + (e % 64) * 2, 16, 1024, 2);
               const uint64_t db = make_smem_desc(sQa + ks * 256, 128, (C::K1 / 8) * 128, 0);
@@ -330,6 +345,9 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               umma_commit(&bars->hid_full[wg]);
             }
             __syncwarp();
+            // the next G1 overwrites LOG / A2 and reads the next query image: the E3 group must have copied the fp16
+            // logits of this query out of A2 and staged that image (a2_read)
+            if (j + 1 < n || (n_next > 0 && C::STAGES > 1)) mbar_wait_sleep(&bars->a2_read[wg], (c1 - 1u) & 1u);
             if (j + 1 < n) {
               issue_g1(s);
             } else if (n_next > 0 && C::STAGES > 1) {  // (single stage: the next tile cannot land before this one is released)
@@ -348,7 +366,11 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (wg == 0) TR(2, 3, c2);
             if (elect_one_sync()) {
 #pragma unroll
+#ifdef MOL_ABLATE_DIAG
+              for (int ks = 0; ks < 1; ++ks) {  // (timing experiment: one SS k-step only)
+#else
               for (int ks = 0; ks < L / 16; ++ks) {  // GATE = GI_tile . diag(0.5 gq)
+#endif
                 const uint64_t da = (L == 64) ? make_smem_desc(sGIa + ks * 32, 16, 1024, 2)
                                               : make_smem_desc(sGIa + ks * 32, 16, 512, 4);
                 const uint64_t db = make_smem_desc(sDa + ks * 256, 128, (L / 8) * 128, 0);
@@ -386,8 +408,9 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
   } else if (warp < kCtlWarp0 && ((warp >> 2) & 1) == 1) {
-    // =============================== E2 warpgroup of slot `wg` ===============================
-    // hidden activations: HID (fp32) -> u -> h = u + u tanh(u) in packed half2 -> A3 (in place) + ones block
+    // =============================== E1 / E2 warpgroup of slot `wg` ===============================
+    // E1: LOG (fp32) -> fp16 operand A2 (in place) + ones block.  E2: HID (fp32) -> u -> h = u + u tanh(u) in packed
+    // half2 -> A3 (in place) + ones block.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kE2Regs));
     const int wg = warp >> 3;
     const uint32_t base = tmem + (uint32_t)wg * 256u + ((uint32_t)((warp & 3) * 32) << 16);
@@ -399,17 +422,74 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     int tile = 0, q = 0;
     uint32_t cnt = 0;
     while (seq.next(tile, q)) {
+      // ---------------- E1
+      if (warp == 4) TR(1, 4, cnt);
+      mbar_wait_sleep(&bars->log_full[wg], cnt & 1u);
+      tc_fence_after();
+      if (warp == 4) TR(1, 5, cnt);
+      {
+        uint32_t la[16], lb[16];
+        auto conv = [&](const uint32_t* v, uint32_t col) __attribute__((always_inline)) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j2 = 0; j2 < 8; ++j2)
+            pk[j2] = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+          tmem_st_x8(base + col, pk);
+        };
+        // chunk c (16 fp32 columns) -> A2 columns [8c, 8c + 8): overwrites LOG columns of chunk c / 2 (in registers)
+        tmem_ld_x16(base + kColLog, la);
+        tmem_ld_x16(base + kColLog + 16, lb);
+        tmem_ld_wait_bind16(la);
+        tmem_ld_wait_bind16(lb);
+        conv(la, kColLog);
+        if constexpr (L == 64) tmem_ld_x16(base + kColLog + 32, la);
+        conv(lb, kColLog + 8);
+        if constexpr (L == 64) {
+          tmem_ld_x16(base + kColLog + 48, lb);
+          tmem_ld_wait_bind16(la);
+          tmem_ld_wait_bind16(lb);
+          conv(la, kColLog + 16);
+          conv(lb, kColLog + 24);
+        }
+        tmem_st_x8(base + kColLog + L / 2, ones);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bars->e1_done[wg]);
+      // ---------------- E2
       if (warp == 4) TR(1, 0, cnt);
       mbar_wait_sleep(&bars->hid_full[wg], cnt & 1u);
       tc_fence_after();
       if (warp == 4) TR(1, 1, cnt);
       uint32_t va[16], vb[16];
-      auto act = [&](const uint32_t* v, uint32_t col) __attribute__((always_inline)) {
+      auto act = [&](const uint32_t* v, uint32_t col, bool poly) __attribute__((always_inline)) {
         uint32_t hk[8];
+        if (poly) {
 #pragma unroll
-        for (int j2 = 0; j2 < 8; ++j2) {
-          const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
-          hk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
+          for (int j2 = 0; j2 < 8; ++j2) {
+            const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+            const float2 c = make_float2(clamp_sym(u.x, kTanhC), clamp_sym(u.y, kTanhC));
+            const float2 s2 = __fmul2_rn(c, c);
+            float2 p = __ffma2_rn(make_float2(kT6, kT6), s2, make_float2(kT5, kT5));
+            p = __ffma2_rn(p, s2, make_float2(kT4, kT4));
+            p = __ffma2_rn(p, s2, make_float2(kT3, kT3));
+            p = __ffma2_rn(p, s2, make_float2(kT2, kT2));
+            p = __ffma2_rn(p, s2, make_float2(kT1, kT1));
+            p = __ffma2_rn(p, s2, make_float2(kT0, kT0));
+            const float2 t = __fmul2_rn(c, p);
+            const float2 h = __ffma2_rn(u, t, u);
+            hk[j2] = pack_f16x2(h.x, h.y);
+          }
+        } else {
+#pragma unroll
+          for (int j2 = 0; j2 < 8; ++j2) {
+            const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+#ifdef MOL_ABLATE_E2
+            hk[j2] = fma_f16x2(u2, u2, u2);
+#else
+            hk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
+#endif
+          }
         }
         tmem_st_x8(base + col, hk);
       };
@@ -420,10 +500,10 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int c = 0; c < 8; c += 2) {
         tmem_ld_wait_bind16(va);
         tmem_ld_x16(base + kColHid + 16 * (c + 1), vb);
-        act(va, kColHid + 8 * c);
+        act(va, kColHid + 8 * c, (kE2PolyMask >> c) & 1u);
         tmem_ld_wait_bind16(vb);
         if (c + 2 < 8) tmem_ld_x16(base + kColHid + 16 * (c + 2), va);
-        act(vb, kColHid + 8 * (c + 1));
+        act(vb, kColHid + 8 * (c + 1), (kE2PolyMask >> (c + 1)) & 1u);
         if (c == 2) {  // first half of A3 (k < 64) is in TMEM: the issuer may start G3
           tmem_st_wait();
           tc_fence_before();
@@ -439,7 +519,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       ++cnt;
     }
   } else if (warp < kCtlWarp0) {
-    // =============================== E1 / E3 warpgroup of slot `wg` ===============================
+    // =============================== E3 warpgroup of slot `wg` (+ query staging) ===============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kE13Regs));
     const int wg = warp >> 3;                 // slot
     const int r = tid & 127;                  // item row within the tile == TMEM lane
@@ -497,42 +577,28 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
     // Stage order of this group: E1(j) -> E3(j-1).  E2(j) runs concurrently in the slot's other warpgroup, the MMAs
     // behind both.  The logits of two queries are live at once, as packed fp16 pairs (pkA / pkB alternate).
+    // Start of a step: once E1 (the slot's other warpgroup) has written the fp16 logits of this query to A2, copy them
+    // to registers (E3 needs them one step later) and stage the next query image (G1 of this query is complete, so the
+    // image buffer is free); a2_read then lets the issuer start the next G1, which overwrites both.
     auto e1 = [&](uint32_t (&pk)[L / 2]) __attribute__((always_inline)) {
       if (warp == 0) TR(0, 0, cnt);
-      mbar_wait_sleep(&bars->log_full[wg], cnt & 1u);
+      mbar_wait_sleep(&bars->e1_done[wg], cnt & 1u);
       tc_fence_after();
       if (warp == 0) TR(0, 1, cnt);
-      {
-        // LOG in chunks of 16 columns, two chunks in flight (keeps the register peak at 2 x 16 + the packed logits)
-        uint32_t la[16], lb[16];
-        tmem_ld_x16(base + kColLog, la);
-        tmem_ld_x16(base + kColLog + 16, lb);
-        // G1 of this query is complete: its image buffer is free for the next query
-        if (have_n) store_image();
-        fence_proxy_async_smem();
-#pragma unroll
-        for (int c = 0; c < L / 16; c += 2) {
-          tmem_ld_wait_bind16(la);
-          tmem_ld_wait_bind16(lb);
-#pragma unroll
-          for (int j2 = 0; j2 < 8; ++j2)
-            pk[8 * c + j2] = pack_f16x2(__uint_as_float(la[2 * j2]), __uint_as_float(la[2 * j2 + 1]));
-          if (c + 2 < L / 16) tmem_ld_x16(base + kColLog + 16 * (c + 2), la);
-#pragma unroll
-          for (int j2 = 0; j2 < 8; ++j2)
-            pk[8 * c + 8 + j2] = pack_f16x2(__uint_as_float(lb[2 * j2]), __uint_as_float(lb[2 * j2 + 1]));
-          if (c + 3 < L / 16) tmem_ld_x16(base + kColLog + 16 * (c + 3), lb);
-        }
-      }
       if constexpr (L == 64) {
-        tmem_st_x32(base + kColLog, pk);
+        tmem_ld_x32(base + kColLog, pk);
       } else {
-        tmem_st_x16(base + kColLog, pk);
+        tmem_ld_x16(base + kColLog, pk);
       }
-      tmem_st_x8(base + kColLog + L / 2, ones);
-      tmem_st_wait();
+      if (have_n) store_image();
+      fence_proxy_async_smem();
+      if constexpr (L == 64) {
+        tmem_ld_wait_bind32(pk);
+      } else {
+        tmem_ld_wait_bind16(pk);
+      }
       tc_fence_before();
-      mbar_arrive(&bars->e1_done[wg]);
+      mbar_arrive(&bars->a2_read[wg]);
       if (warp == 0) TR(0, 2, cnt);
     };
 
@@ -558,7 +624,11 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             u.y = fminf(u.y, kGateClamp);
           }
           const float2 a = __fmul2_rn(u, l2e2);
+#ifdef MOL_ABLATE_E3
+          const float2 t = u;
+#else
           const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+#endif
           const float2 x = __ffma2_rn(a, t, a);  // w * log2(e), in [-0.41, 116]
           float2 e;
           if ((j2 & 3) < kEx2EmuOf4) {
@@ -573,7 +643,11 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             e.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(m.x) << 23));
             e.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(m.y) << 23));
           } else {
+#ifdef MOL_ABLATE_E3
+            e = x;
+#else
             e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+#endif
           }
           den[j2 & 3] = __fadd2_rn(den[j2 & 3], e);
           num[j2 & 3] = __ffma2_rn(e, __half22float2(*reinterpret_cast<const __half2*>(&lgc[j2])), num[j2 & 3]);

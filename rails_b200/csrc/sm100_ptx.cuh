@@ -266,6 +266,12 @@ __device__ __forceinline__ uint32_t fma_f16x2(uint32_t a, uint32_t b, uint32_t c
   asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
+// sign(x) * min(|x|, c) for c > 0: a symmetric clamp in one ALU instruction
+__device__ __forceinline__ float clamp_sym(float x, float c) {
+  float y;
+  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(c));
+  return y;
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
