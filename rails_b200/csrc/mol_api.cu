@@ -155,7 +155,7 @@ static bool use_tensor(const mol_shape_t& s, int mode) {
   return coarse_supported(s);
 }
 
-constexpr int64_t kFilterMinItems = 1 << 18;
+constexpr int64_t kFilterMinItems = 1 << 16;
 
 static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, void* base,
                        size_t cap, SearchWs* ws) {

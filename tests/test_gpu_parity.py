@@ -228,6 +228,24 @@ def test_filter_strategy_survives_adversarial_item_order(order):
     assert (s - s_ex).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("N,B,k", [(400_003, 2, 2500), (262_144, 1, 1), (999_963, 3, 200)])
+def test_filter_strategy_edge_sizes_match_exact_mode(N, B, k):
+    """Large k (capacity 4 K' > 4096), ragged last tile, single query, k = 1 on the fused-filter strategy: the tensor
+    path must return exactly what the fp32 exact mode returns."""
+    cfg = CFG_8x8x32
+    mol, _ = build_module(cfg, None, DEV, seed=31)
+    items, ids, q, _ = synthetic_inputs(cfg, N, B, 31, DEV)
+    a = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=_lib.MODE_AUTO)
+    e = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=_lib.MODE_EXACT)
+    s, i = a(q, k=k)
+    s_ex, i_ex = e(q, k=k)
+    same = (i == i_ex).float().mean().item()
+    assert (s - s_ex).abs().max().item() < 1e-4
+    if same < 1.0:  # only exact ties / fp32-reordered near-ties may differ
+        bad = (i != i_ex)
+        assert (s[bad] - s_ex[bad]).abs().max().item() < 1e-5, same
+
+
 # ------------------------------------------------------------------------------- tensor-core coarse pass
 @pytest.mark.parametrize(
     "cfg,N,B,seed",
