@@ -4,7 +4,7 @@
 //   rails/similarities/mol/similarity_fn.py:389-405   logits = <Q_sub[n], X_sub[m]> / tau
 //   rails/similarities/mol/similarity_fn.py:166-179   G = GQ*GI + W2 silu(W1 l + b1) + b2 ; w = G sigmoid(G)
 //   rails/similarities/mol/similarity_fn.py:42-46     p = softmax(w); p /= clamp(sum p, eps); score = sum p*l
-// It serves three roles: (1) the rescoring pass that turns the tensor-core pass' bf16 candidates into
+// It serves three roles: (1) the rescoring pass that turns the tensor-core pass' fp16 candidates into
 // reference-exact fp32 scores/order, (2) MOL_MODE_EXACT brute force / MoLSimilarity.forward's (B, N)
 // score matrix, (3) the per-query fallback when the coarse pass' safety check fails.
 //
