@@ -194,6 +194,20 @@ int mol_search_avg(const mol_shape_t* shape, const mol_weights_t* w, const mol_i
                    float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                    mol_stream_t stream);
 
+/* MoLNaiveTopK / MoLCombTopK (rails/indexing/mol_top_k.py:133-293 and :432-551): for every
+ * (query group n, item group m) the k_per_group items with the largest fp32 <Q_sub[b,n], X_sub[x,m]> (the reference keeps
+ * the item operand in bf16), plus - Comb only, avg_top_k > 0 - the avg_top_k items of MoLAvgTopK.topk_ids; the union is
+ * sorted by position, scored with exact fp32 MoL, duplicates get the reference's -32767 sentinel, and ALL
+ * C = P_Q * P_X * k_per_group + avg_top_k candidates come back sorted by score (the reference overwrites the caller's k
+ * with C, :256 / :518).  out_scores (B, C) fp32, out_ids (B, C) int64.  avg_items may be NULL when avg_top_k == 0.
+ * FAISS (use_faiss=True) is out of scope. */
+int mol_search_groups_workspace_bytes(const mol_shape_t* shape, int64_t num_items, int32_t B, int32_t k_per_group,
+                                      int32_t avg_top_k, size_t* bytes);
+int mol_search_groups(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
+                      const float* avg_items, const float* queries, const int64_t* user_ids, int32_t B,
+                      int32_t k_per_group, int32_t avg_top_k, float* out_scores, int64_t* out_ids, void* workspace,
+                      size_t workspace_bytes, mol_stream_t stream);
+
 /* Optional CUDA-event timing of the dominant scoring kernel (the tcgen05 coarse pass, or the fp32
  * kernel in MOL_MODE_EXACT) on the stream it is launched on: enable, run searches, collect the summed
  * device time and the number of timed launches (collect synchronises on the recorded events). */

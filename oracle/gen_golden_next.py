@@ -83,9 +83,53 @@ def avg_case(name, cfg, N, B, k, avg_top_k, seed):
           float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(i_f32, i_bf16)])))
 
 
+def groups_case(name, cfg, N, B, k_per_group, avg_top_k, seed):
+    """Reference MoLNaiveTopK (avg_top_k == 0; mol_top_k.py:133-293) / MoLCombTopK (:432-551).  Stored twice, as avg_case."""
+    import json
+
+    from oracle.reference_loader import build_reference_mol
+    from rails.indexing.mol_top_k import MoLCombTopK, MoLNaiveTopK
+    from tests.helpers import synthetic_inputs
+
+    torch.manual_seed(seed)
+    mol = build_reference_mol(cfg).eval()
+    items, ids, q, uid = synthetic_inputs(cfg, N, B, seed)
+    kw = {} if uid is None else {"user_ids": uid}
+    with torch.inference_mode():
+        if avg_top_k > 0:
+            top = MoLCombTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), avg_top_k, k_per_group)
+        else:
+            top = MoLNaiveTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), k_per_group)
+        s_bf16, i_bf16 = top(q, k=10, **kw)
+        comp, _ = mol.get_item_component_embeddings(items, decoupled_inference=True)
+        comp = comp.float()
+        P_X, D_P = comp.size(1), comp.size(2)
+        top._mol_item_embeddings = comp
+        top._mol_item_embeddings_t = comp.permute(1, 0, 2).reshape(-1, D_P).transpose(0, 1)
+        if avg_top_k > 0:
+            top._avg_top_k_module._mol_item_embeddings = comp
+            top._avg_top_k_module._avg_mol_item_embeddings_t = (comp.sum(1) / P_X).transpose(0, 1)
+        s_f32, i_f32 = top(q, k=10, **kw)
+    out = {f"sd::{k_}": v.detach().numpy() for k_, v in mol.state_dict().items()}
+    out.update(
+        cfg=np.frombuffer(json.dumps(cfg.to_json()).encode(), dtype=np.uint8), items=items.numpy(), item_ids=ids.numpy(),
+        queries=q.numpy(), k_per_group=np.int64(k_per_group), avg_top_k=np.int64(avg_top_k),
+        ref_scores_f32=s_f32.numpy(), ref_ids_f32=i_f32.numpy(), ref_scores_bf16=s_bf16.float().numpy(), ref_ids_bf16=i_bf16.numpy(),
+    )
+    if uid is not None:
+        out["user_ids"] = uid.numpy()
+    np.savez_compressed(os.path.join(OUT, f"next_{name}.npz"), **out)
+    n_valid = (s_f32 > -32767.0).sum(1)
+    print(name, tuple(i_f32.shape), "distinct candidates per query:", n_valid.tolist())
+
+
 if __name__ == "__main__":
     from tests.helpers import CFG_8x8x32, CFG_8x4x64
 
+    groups_case("naive_8x8x32", CFG_8x8x32, N=3000, B=4, k_per_group=5, avg_top_k=0, seed=21)
+    groups_case("naive_8x4x64_uid", CFG_8x4x64, N=1200, B=3, k_per_group=10, avg_top_k=0, seed=22)
+    groups_case("comb_8x8x32", CFG_8x8x32, N=3000, B=4, k_per_group=5, avg_top_k=100, seed=23)
+    groups_case("comb_8x4x64_uid", CFG_8x4x64, N=1200, B=3, k_per_group=4, avg_top_k=50, seed=24)
     avg_case("avg_8x8x32", CFG_8x8x32, N=4000, B=5, k=20, avg_top_k=200, seed=11)
     avg_case("avg_8x4x64_uid", CFG_8x4x64, N=1500, B=4, k=10, avg_top_k=64, seed=12)
     case("mask_basic", N=500, D=16, B=6, k=10, n0=12, seed=1)

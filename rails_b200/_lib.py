@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "mol_merge_topk", "mol_topk_workspace_bytes", "mol_topk", "mol_launch_count", "mol_launch_count_reset",
     "mol_profile_enable", "mol_profile_collect", "mol_select_valid", "mol_mips_workspace_bytes", "mol_mips_search",
     "mol_dot_scores", "mol_index_avg_embeddings", "mol_search_avg_workspace_bytes", "mol_search_avg",
+    "mol_search_groups_workspace_bytes", "mol_search_groups",
 )
 
 
@@ -135,6 +136,11 @@ def load() -> ctypes.CDLL:
     lib.mol_index_avg_embeddings.argtypes = [P(MolShape), P(MolIndex), c_void_p, c_void_p]
     lib.mol_search_avg_workspace_bytes.argtypes = [P(MolShape), c_int64, c_int32, c_int32, c_int32, P(c_size_t)]
     lib.mol_search_avg.argtypes = [
+        P(MolShape), P(MolWeights), P(MolIndex), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
+    ]
+    lib.mol_search_groups_workspace_bytes.argtypes = [P(MolShape), c_int64, c_int32, c_int32, c_int32, P(c_size_t)]
+    lib.mol_search_groups.argtypes = [
         P(MolShape), P(MolWeights), P(MolIndex), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
     ]

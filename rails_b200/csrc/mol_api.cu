@@ -738,6 +738,202 @@ int mol_search_avg(const mol_shape_t* shape, const mol_weights_t* w, const mol_i
                                  index->item_ids, nullptr, st);
 }
 
+}  // extern "C"
+namespace mol {
+// ---- MoLNaiveTopK / MoLCombTopK (rails/indexing/mol_top_k.py:133-293, 432-551) ------
+// Per (query b, query group n, item group m): the k_per_group items with the largest <Q_sub[b,n], X_sub[x,m]>; the
+// union over the L groups (plus, for Comb, the avg_top_k items of the averaged-embedding prefilter) is sorted by
+// position, scored with exact fp32 MoL, duplicates are masked to -32767 and ALL C candidates are returned sorted
+// by score (the reference overwrites k with C, mol_top_k.py:256 / :518).
+constexpr float kDupScore = -32767.0f;  // mol_top_k.py:280 / :542
+
+// One block per query: gathers the C candidate positions (P_X pieces of P_Q * kpg from the per-item-group selections
+// + the avg piece) and sorts them ascending in shared memory (torch.sort at mol_top_k.py:252 / :514).
+__global__ void __launch_bounds__(256)
+union_sort_kernel(const int32_t* __restrict__ group_idx, const int32_t* __restrict__ avg_idx, int B, int Px, int per_m,
+                  int avg_top_k, int C, int C2, int32_t* __restrict__ out_sorted) {
+  extern __shared__ int32_t us_smem[];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < C2; i += blockDim.x) {
+    int32_t v = 0x7fffffff;
+    if (i < Px * per_m) {
+      const int m = i / per_m, j = i - m * per_m;
+      v = group_idx[((size_t)m * B + b) * per_m + j];
+    } else if (i < C) {
+      v = avg_idx[(size_t)b * avg_top_k + (i - Px * per_m)];
+    }
+    us_smem[i] = v;
+  }
+  __syncthreads();
+  for (int size = 2; size <= C2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < C2 / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const int32_t a = us_smem[lo], c = us_smem[hi];
+        if ((a > c) == up) {
+          us_smem[lo] = c;
+          us_smem[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) out_sorted[(size_t)b * C + i] = us_smem[i];
+}
+
+// candidate_is_valid (mol_top_k.py:271-280 / :533-542): a candidate equal to its left neighbour is a duplicate
+__global__ void mask_duplicates_kernel(const int32_t* __restrict__ sorted_idx, float* __restrict__ scores, int64_t total,
+                                       int C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (i % C != 0 && sorted_idx[i] == sorted_idx[i - 1]) scores[i] = kDupScore;
+}
+
+struct GroupsWs {
+  float *pre, *h, *proj, *hq, *qsub, *gq, *w1t, *w2t, *qavg, *scores, *seg_scores, *sel_scores, *exact;
+  int32_t *seg_idx, *group_idx, *avg_idx, *sorted_idx;
+  int rows;  // rows of the (rows, N) dot-product matrix scored per launch (a multiple of P_Q)
+  size_t total;
+};
+
+static int plan_groups(const mol_shape_t& s, int64_t N, int B, int kpg, int avg_top_k, void* base, size_t cap,
+                       GroupsWs* ws) {
+  Dims D = dims_of(s);
+  Arena a(base, cap);
+  ws->pre = a.take<float>((size_t)B * 2 * D.Hq);
+  ws->h = a.take<float>((size_t)B * D.Hq);
+  ws->proj = a.take<float>((size_t)B * D.Pq_proj * D.d);
+  ws->hq = a.take<float>((size_t)B * D.Hgq);
+  ws->qsub = a.take<float>((size_t)B * D.Pq * D.d);
+  ws->gq = a.take<float>((size_t)B * D.L);
+  ws->w1t = a.take<float>((size_t)D.L * D.H);
+  ws->w2t = a.take<float>((size_t)D.L * D.H);
+  ws->qavg = a.take<float>((size_t)B * D.d);
+  const int64_t n = N > 0 ? N : 1;
+  int64_t rows = (int64_t)(2ull << 30) / (int64_t)(sizeof(float) * (size_t)n);
+  rows = rows / D.Pq * D.Pq;
+  if (rows < D.Pq) rows = D.Pq;
+  if (rows > (int64_t)B * D.Pq) rows = (int64_t)B * D.Pq;
+  ws->rows = (int)rows;
+  ws->scores = a.take<float>((size_t)rows * (size_t)n);
+  const int kmax = kpg > avg_top_k ? kpg : avg_top_k;
+  const size_t seg = (size_t)(rows + 2 * 148 + 1) * (size_t)kmax;
+  ws->seg_scores = a.take<float>(seg);
+  ws->seg_idx = a.take<int32_t>(seg);
+  ws->sel_scores = a.take<float>((size_t)rows * kmax);
+  const size_t C = (size_t)D.L * kpg + avg_top_k;
+  ws->group_idx = a.take<int32_t>((size_t)B * D.L * kpg);
+  ws->avg_idx = a.take<int32_t>((size_t)B * (avg_top_k > 0 ? avg_top_k : 1));
+  ws->sorted_idx = a.take<int32_t>((size_t)B * C);
+  ws->exact = a.take<float>((size_t)B * C);
+  ws->total = align_up(a.off, 256);
+  if (base != nullptr && a.off > cap) {
+    set_error("workspace too small: need %zu bytes, got %zu", ws->total, cap);
+    return MOL_ERR_WORKSPACE;
+  }
+  return MOL_OK;
+}
+
+// top-kk column positions (int32) of every row of a (nb, N) matrix
+static int select_positions(const GroupsWs& ws, int64_t N, int nb, int kk, int32_t* out_idx, cudaStream_t st) {
+  const int S = select_num_segments(N, nb, kk);
+  const float* sel = ws.scores;
+  const int32_t* pay = nullptr;
+  int64_t sn = N;
+  if (S > 1) {
+    MOL_TRY(launch_select_segments(ws.scores, N, N, nb, S, kk, ws.seg_scores, ws.seg_idx, nullptr, st));
+    sel = ws.seg_scores;
+    pay = ws.seg_idx;
+    sn = (int64_t)S * kk;
+  }
+  return launch_select_final_i32(sel, pay, sn, sn, nb, kk, ws.sel_scores, out_idx, nullptr, nullptr, nullptr, st);
+}
+
+}  // namespace mol
+using namespace mol;
+extern "C" {
+
+int mol_search_groups_workspace_bytes(const mol_shape_t* shape, int64_t num_items, int32_t B, int32_t k_per_group,
+                                      int32_t avg_top_k, size_t* bytes) {
+  MOL_TRY(check_shape(shape));
+  MOL_CHECK_ARG(bytes && B >= 0 && k_per_group >= 1 && avg_top_k >= 0 && num_items >= 0, "bad arguments");
+  GroupsWs ws;
+  MOL_TRY(plan_groups(*shape, num_items, B > 0 ? B : 1, k_per_group, avg_top_k, nullptr, 0, &ws));
+  *bytes = ws.total + 256;
+  return MOL_OK;
+}
+
+int mol_search_groups(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
+                      const float* avg_items, const float* queries, const int64_t* user_ids, int32_t B,
+                      int32_t k_per_group, int32_t avg_top_k, float* out_scores, int64_t* out_ids, void* workspace,
+                      size_t workspace_bytes, mol_stream_t stream) {
+  MOL_TRY(check_shape(shape));
+  MOL_TRY(check_weights(shape, w));
+  MOL_CHECK_ARG(index && index->xsub_f32 && index->gi_f32, "index not laid out");
+  MOL_CHECK_ARG(B >= 0 && k_per_group >= 1 && avg_top_k >= 0, "bad arguments");
+  MOL_CHECK_ARG(avg_top_k == 0 || avg_items, "avg embeddings missing (mol_index_avg_embeddings)");
+  Dims D = dims_of(*shape);
+  const int64_t N = index->num_items;
+  const int64_t C64 = (int64_t)D.L * k_per_group + avg_top_k;
+  MOL_CHECK_ARG(C64 <= MOL_MAX_K, "P_Q * P_X * k_per_group + avg_top_k = %lld exceeds MOL_MAX_K=%d", (long long)C64,
+                MOL_MAX_K);
+  if (k_per_group > N || avg_top_k > N) {
+    set_error("selected index k out of range (k_per_group=%d / avg_top_k=%d > %lld items)", k_per_group, avg_top_k,
+              (long long)N);
+    return MOL_ERR_RANGE;
+  }
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(queries && out_scores && out_ids && workspace, "NULL buffer");
+  MOL_CHECK_ARG(shape->num_uid_tables == 0 || user_ids, "user_ids required when uid embeddings are configured");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = (int)C64;
+  GroupsWs ws;
+  MOL_TRY(plan_groups(*shape, N, B, k_per_group, avg_top_k, workspace, workspace_bytes, &ws));
+  MOL_TRY(run_query_prologue(*shape, *w, queries, user_ids, B, ws.pre, ws.h, ws.proj, ws.hq, ws.qsub, ws.gq, st));
+  MOL_TRY(launch_transpose(w->qi_w1, ws.w1t, D.H, D.L, st));
+  MOL_TRY(launch_transpose(w->qi_w2, ws.w2t, D.L, D.H, st));
+  // per-group dot products and their top k_per_group positions (mol_top_k.py:239-249 / :501-511): for item group m,
+  // rows (b, n) of Q_sub against X_sub[:, m, :] (row stride P_X * d inside the fp32 cache)
+  const int per_m = D.Pq * k_per_group;
+  const int qrows = ws.rows / D.Pq;  // queries per launch
+  for (int m = 0; m < D.Px; ++m) {
+    for (int b0 = 0; b0 < B; b0 += qrows) {
+      const int nq = (B - b0 < qrows) ? (B - b0) : qrows;
+      const int nb = nq * D.Pq;
+      MOL_TRY(launch_linear(ws.qsub + (size_t)b0 * D.Pq * D.d, index->xsub_f32 + (size_t)m * D.d, nullptr, ws.scores, nb,
+                            (int)N, D.d, (int64_t)D.Px * D.d, 1, ACT_NONE, st));
+      MOL_TRY(select_positions(ws, N, nb, k_per_group, ws.group_idx + ((size_t)m * B + b0) * per_m, st));
+    }
+  }
+  if (avg_top_k > 0) {  // MoLAvgTopK.topk_ids (:387-429): mean over the query groups . mean over the item groups
+    const int64_t total = (int64_t)B * D.d;
+    avg_groups_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.qsub, ws.qavg, B, D.Pq, D.d, 1.0f / D.Pq);
+    MOL_LAUNCH_CHECK();
+    for (int b0 = 0; b0 < B; b0 += ws.rows) {
+      const int nb = (B - b0 < ws.rows) ? (B - b0) : ws.rows;
+      MOL_TRY(launch_linear(ws.qavg + (size_t)b0 * D.d, avg_items, nullptr, ws.scores, nb, (int)N, D.d, D.d, 1, ACT_NONE, st));
+      MOL_TRY(select_positions(ws, N, nb, avg_top_k, ws.avg_idx + (size_t)b0 * avg_top_k, st));
+    }
+  }
+  int C2 = 1;
+  while (C2 < C) C2 <<= 1;
+  union_sort_kernel<<<B, 256, (size_t)C2 * sizeof(int32_t), st>>>(ws.group_idx, ws.avg_idx, B, D.Px, per_m, avg_top_k, C,
+                                                                  C2, ws.sorted_idx);
+  MOL_LAUNCH_CHECK();
+  // exact MoL on the union (:257-270), duplicate mask (:271-280), all C candidates sorted by score + id map (:281-292)
+  MOL_TRY(launch_exact_scores(*shape, *w, *index, ws.w1t, ws.w2t, ws.qsub, ws.gq, B, ws.sorted_idx, C, C, ws.exact,
+                              nullptr, st));
+  {
+    const int64_t total = (int64_t)B * C;
+    mask_duplicates_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.sorted_idx, ws.exact, total, C);
+    MOL_LAUNCH_CHECK();
+  }
+  return launch_select_final_i32(ws.exact, ws.sorted_idx, C, C, B, C, out_scores, nullptr, out_ids, index->item_ids,
+                                 nullptr, st);
+}
+
 int mol_query_prologue(const mol_shape_t* shape, const mol_weights_t* w, const float* queries,
                        const int64_t* user_ids, int32_t B, float* out_qsub, float* out_gq,
                        void* workspace, size_t workspace_bytes, mol_stream_t stream) {

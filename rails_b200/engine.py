@@ -366,6 +366,44 @@ def search_avg(
     return out_s, out_i
 
 
+def search_groups(
+    weights: PackedWeights,
+    index: IndexHandle,
+    avg_items: Optional[torch.Tensor],
+    workspace: Workspace,
+    queries: torch.Tensor,
+    user_ids: Optional[torch.Tensor],
+    k_per_group: int,
+    avg_top_k: int,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """mol_search_groups: MoLNaiveTopK.forward (avg_top_k == 0) / MoLCombTopK.forward on the GPU.
+    Returns (scores (B, C) fp32, ids (B, C) int64) with C = P_Q * P_X * k_per_group + avg_top_k."""
+    lib = _lib.load()
+    _require_cuda(queries, "query_embeddings")
+    dev = index.device
+    q = queries.detach().to(device=dev, dtype=torch.float32).contiguous()
+    B = int(q.size(0))
+    uid = None
+    if weights.shape.num_uid_tables > 0:
+        if user_ids is None:
+            raise KeyError("user_ids")
+        uid = user_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
+    C = weights.shape.query_dot_product_groups * weights.shape.item_dot_product_groups * k_per_group + avg_top_k
+    out_s = torch.empty((B, C), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, C), dtype=torch.int64, device=dev)
+    nbytes = c_size_t()
+    _lib.check(lib.mol_search_groups_workspace_bytes(byref(weights.shape), index.N, B, k_per_group, avg_top_k, byref(nbytes)))
+    ws = workspace.get(nbytes.value)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.mol_search_groups(
+                byref(weights.shape), byref(weights.struct), byref(index.struct), _ptr(avg_items), _ptr(q), _ptr(uid),
+                B, k_per_group, avg_top_k, _ptr(out_s), _ptr(out_i), _ptr(ws), ws.numel(), _stream_ptr(dev),
+            )
+        )
+    return out_s, out_i
+
+
 def avg_item_embeddings(weights: PackedWeights, index: IndexHandle) -> torch.Tensor:
     """(N, d) fp32 mean over the P_X item sub-embeddings (MoLAvgTopK's prefilter operand)."""
     lib = _lib.load()

@@ -153,3 +153,67 @@ class MoLAvgTopK(MoLTopKModule):
             kwargs.get("user_ids"), int(k), self._avg_top_k,
         )
         return scores.to(query_embeddings.dtype), ids
+
+
+class MoLNaiveTopK(MoLTopKModule):
+    """Greedy per-group top-k of the reference (mol_top_k.py:133-293): for each of the P_Q x P_X embedding-set pairs the
+    `k_per_group` items with the largest dot product, the union scored with exact MoL.  As in the reference, `k` is
+    ignored: all P_Q * P_X * k_per_group candidates come back sorted by score, duplicates carrying the -32767 sentinel
+    (:256, :271-292).  One `mol_search_groups` call; the dot products are fp32 (the reference's default is bf16
+    component embeddings, :37).  SURVEY.md §8 row f3."""
+
+    def __init__(
+        self,
+        mol_module: MoLSimilarity,
+        item_embeddings: torch.Tensor,
+        item_ids: torch.Tensor,
+        k_per_group: int,
+        use_faiss: bool = False,
+    ) -> None:
+        if use_faiss:
+            raise NotImplementedError("use_faiss=True: FAISS is outside the B200 hot path (DESIGN.md §7)")
+        super().__init__(
+            mol_module=mol_module,
+            item_embeddings=item_embeddings,
+            item_ids=item_ids,
+            flatten_item_ids_and_embeddings=True,
+            keep_component_level_item_embeddings=False,
+        )
+        self._k_per_group: int = int(k_per_group)
+        self._use_faiss: bool = False
+
+    @torch.no_grad()
+    def forward(self, query_embeddings: torch.Tensor, k: int, sorted: bool = True, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        index = self._ensure_index()
+        dev = index.device
+        scores, ids = engine.search_groups(
+            self._mol_module.packed_weights(dev), index, None, self._mol_module.workspace(dev), query_embeddings,
+            kwargs.get("user_ids"), self._k_per_group, 0,
+        )
+        return scores.to(query_embeddings.dtype), ids
+
+
+class MoLCombTopK(MoLAvgTopK):
+    """MoLNaiveTopK's per-group candidates plus MoLAvgTopK's prefilter candidates (mol_top_k.py:432-551); returns all
+    P_Q * P_X * k_per_group + avg_top_k candidates sorted by exact MoL score (:518, :533-551)."""
+
+    def __init__(
+        self,
+        mol_module: MoLSimilarity,
+        item_embeddings: torch.Tensor,
+        item_ids: torch.Tensor,
+        avg_top_k: int,
+        k_per_group: int,
+    ) -> None:
+        super().__init__(mol_module, item_embeddings, item_ids, avg_top_k)
+        self._k_per_group: int = int(k_per_group)
+
+    @torch.no_grad()
+    def forward(self, query_embeddings: torch.Tensor, k: int, sorted: bool = True, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        index, avg = self._ensure_avg()
+        dev = index.device
+        scores, ids = engine.search_groups(
+            self._mol_module.packed_weights(dev), index, avg, self._mol_module.workspace(dev), query_embeddings,
+            kwargs.get("user_ids"), self._k_per_group, self._avg_top_k,
+        )
+        return scores.to(query_embeddings.dtype), ids
