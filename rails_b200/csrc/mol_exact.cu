@@ -8,9 +8,12 @@
 // reference-exact fp32 scores/order, (2) MOL_MODE_EXACT brute force / MoLSimilarity.forward's (B, N)
 // score matrix, (3) the per-query fallback when the coarse pass' safety check fails.
 //
-// Mapping: blockIdx.y = query; each warp takes groups of PT=8 items of that query.  A lane owns logit
-// indices {lane + 32*ll} and hidden units {lane + 32*jj}; the two MLP layers are register-tiled
-// (PT x LL / PT x HH accumulators per lane) with the transposed weights broadcast from shared memory.
+// Mapping: persistent blocks (one per SM) stage the qi-MLP weights in shared memory ONCE; the flat list of work items
+// (active query, group of PT=8 items) is split into one contiguous range per warp, so a warp re-stages its query
+// (Q_sub, gq) only when the query changes.  A lane owns logit indices {lane + 32*ll} and hidden units {lane + 32*jj};
+// the two MLP layers are register-tiled (PT x LL / PT x HH accumulators per lane) with the transposed weights
+// broadcast from shared memory.  The item rows of the NEXT work item are prefetched into L2 while the MLP of the
+// current one runs (the candidates of the rescoring pass are random rows: without it every pass waits on DRAM).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -18,8 +21,9 @@
 namespace mol {
 
 constexpr int PT = 8;            // items per warp pass
-constexpr int EX_WARPS = 8;      // warps per block
-constexpr int EX_THREADS = EX_WARPS * 32;
+#ifndef EXACT_NW_SMALL
+#define EXACT_NW_SMALL 8      // warps per block for L <= 64 (staged rows: 8 x 18.8 KB + 64 KB of weights)
+#endif
 
 struct ExactParams {
   const float* qsub;   // (B, Pq, d)
@@ -34,10 +38,10 @@ struct ExactParams {
   const int32_t* query_flags;  // nullable
   float* scores;
   int64_t N, n_per_query, ld;
+  int B;
   int Pq, Px, d, L, H;
   float temperature, eps;
   int renorm;
-  int w_in_smem;
 };
 
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows,
@@ -48,86 +52,213 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
   out[c * rows + r] = in[i];
 }
 
-template <int LL, int HH>
-__global__ void __launch_bounds__(EX_THREADS) exact_scores_kernel(ExactParams P) {
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Warp-uniform walk over the ACTIVE queries (query_flags[b] != 0, or all of them): seek(a) positions on the a-th
+// active query, next() moves to the following one.  All lanes hold the same state.
+struct ActiveQueries {
+  const int32_t* flags;
+  int B, lane;
+  int b;  // current query (B when exhausted)
+  __device__ ActiveQueries(const int32_t* f, int B_, int lane_) : flags(f), B(B_), lane(lane_), b(-1) {}
+  __device__ int count() const {
+    if (!flags) return B;
+    int c = 0;
+    for (int i = 0; i < B; i += 32) {
+      const int q = i + lane;
+      c += __popc(__ballot_sync(0xffffffffu, q < B && flags[q] != 0));
+    }
+    return c;
+  }
+  __device__ void seek(int a) {
+    if (!flags) {
+      b = a < B ? a : B;
+      return;
+    }
+    int seen = 0;
+    for (int i = 0; i < B; i += 32) {
+      const int q = i + lane;
+      const unsigned m = __ballot_sync(0xffffffffu, q < B && flags[q] != 0);
+      const int c = __popc(m);
+      if (seen + c > a) {  // the a-th active query is in this word: its (a - seen)-th set bit
+        unsigned mm = m;
+        for (int t = 0; t < a - seen; ++t) mm &= mm - 1;
+        b = i + __ffs(mm) - 1;
+        return;
+      }
+      seen += c;
+    }
+    b = B;
+  }
+  __device__ void next() {
+    if (!flags) {
+      b = b + 1 < B ? b + 1 : B;
+      return;
+    }
+    int q0 = b + 1;
+    for (int i = q0 & ~31; i < B; i += 32) {
+      const int q = i + lane;
+      const unsigned m = __ballot_sync(0xffffffffu, q >= q0 && q < B && flags[q] != 0);
+      if (m) {
+        b = i + __ffs(m) - 1;
+        return;
+      }
+    }
+    b = B;
+  }
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// WS: the transposed qi-MLP weights live in shared memory (else they are read through L1 from global memory).
+// ST: the X_sub rows of a work item are staged in shared memory by cp.async, one work item ahead (else __ldg).
+template <int LL, int HH, int NW, bool WS, bool ST>
+__global__ void __launch_bounds__(NW * 32) exact_scores_kernel(ExactParams P) {
   extern __shared__ __align__(16) float smem[];
-  const int L = LL * 32, H = HH * 32;
-  const int b = blockIdx.y;
-  if (P.query_flags && P.query_flags[b] == 0) return;
+  constexpr int L = LL * 32, H = HH * 32;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int d = P.d, Pq = P.Pq, Px = P.Px;
   const int qstride = d + 4;
 
-  // ---- carve shared memory
+  // ---- this warp's contiguous range of (active query, item group) work items; blocks without work leave before
+  //      staging anything (the fallback launches usually have no active query at all)
+  ActiveQueries aq(P.query_flags, P.B, lane);
+  const int64_t groups = (P.n_per_query + PT - 1) / PT;
+  const int64_t T = (int64_t)aq.count() * groups;
+  const int64_t W = (int64_t)gridDim.x * NW, gw = (int64_t)blockIdx.x * NW + warp;
+  if (T * ((int64_t)blockIdx.x * NW) / W >= T * ((int64_t)(blockIdx.x + 1) * NW) / W) return;  // block-uniform
+  int64_t t = T * gw / W;
+  const int64_t t1 = T * (gw + 1) / W;
+
+  // ---- carve shared memory: [W1t | W2t] | b1 | b2 | per warp: gq, Q_sub, logits^T, hidden^T, staged item rows
   float* sp = smem;
-  const float* W1t;
-  const float* W2t;
-  if (P.w_in_smem) {
-    float* a = sp;
-    sp += L * H;
-    float* c = sp;
-    sp += H * L;
-    for (int i = threadIdx.x; i < L * H; i += EX_THREADS) {
-      a[i] = P.w1t[i];
-      c[i] = P.w2t[i];
+  float* W1s = sp;
+  float* W2s = sp + (WS ? L * H : 0);
+  if (WS) {
+    sp += 2 * L * H;
+    for (int i = threadIdx.x; i < L * H / 4; i += NW * 32) {
+      reinterpret_cast<float4*>(W1s)[i] = __ldg(reinterpret_cast<const float4*>(P.w1t) + i);
+      reinterpret_cast<float4*>(W2s)[i] = __ldg(reinterpret_cast<const float4*>(P.w2t) + i);
     }
-    W1t = a;
-    W2t = c;
-  } else {
-    W1t = P.w1t;
-    W2t = P.w2t;
   }
   float* b1s = sp;
   sp += H;
   float* b2s = sp;
   sp += L;
-  float* gqs = sp;
-  sp += L;
-  float* Qs = sp;
-  sp += Pq * qstride;
-  float* logT = sp + warp * (L + H) * PT;  // [L][PT]
-  float* hidT = logT + L * PT;             // [H][PT]
+  const int xrow = Px * qstride;  // staged item row: Px groups of d floats, padded like Q_sub (bank-conflict-free)
+  float* wsm = sp + (size_t)warp * (L + Pq * qstride + (L + H) * PT + (ST ? PT * xrow : 0));
+  float* gqs = wsm;                    // [L]
+  float* Qs = gqs + L;                 // [Pq][qstride]
+  float* logT = Qs + Pq * qstride;     // [L][PT]
+  float* hidT = logT + L * PT;         // [H][PT]
+  float* Xst = hidT + H * PT;          // [PT][Px][qstride]   (ST only)
 
-  for (int i = threadIdx.x; i < H; i += EX_THREADS) b1s[i] = P.b1[i];
-  for (int i = threadIdx.x; i < L; i += EX_THREADS) {
-    b2s[i] = P.b2[i];
-    gqs[i] = P.gq[(int64_t)b * L + i];
-  }
-  for (int i = threadIdx.x; i < Pq * d; i += EX_THREADS)
-    Qs[(i / d) * qstride + (i % d)] = P.qsub[(int64_t)b * Pq * d + i];
+  for (int i = threadIdx.x; i < H; i += NW * 32) b1s[i] = P.b1[i];
+  for (int i = threadIdx.x; i < L; i += NW * 32) b2s[i] = P.b2[i];
   __syncthreads();
+  if (t >= t1) return;
+  int64_t g = t % groups;
+  aq.seek((int)(t / groups));
+  int staged = -1;
 
-  const int64_t groups = (P.n_per_query + PT - 1) / PT;
-  for (int64_t g = (int64_t)blockIdx.x * EX_WARPS + warp; g < groups;
-       g += (int64_t)gridDim.x * EX_WARPS) {
+  auto item_of = [&](int b, int64_t j) -> int64_t {  // -1: padding / out of range
+    if (j >= P.n_per_query) return -1;
+    const int64_t x = P.cand ? (int64_t)P.cand[(int64_t)b * P.ld + j] : j;
+    return (x >= 0 && x < P.N) ? x : -1;
+  };
+  const int cpr = Px * d / 4;  // 16-byte chunks per item row
+  const int d4 = d / 4;
+  // lane p < PT holds the item of slot p of a work item; `stage_rows` starts the copy of those rows into Xst
+  auto stage_rows = [&](int64_t mine) {
+    for (int c0 = 0; c0 < PT * cpr; c0 += 32) {  // warp-uniform trip count (the shuffle needs every lane)
+      const int c = c0 + lane;
+      const int p = min(c / cpr, PT - 1), r = c - p * cpr;
+      const int64_t x = __shfl_sync(0xffffffffu, mine, p);
+      const int m = r / d4, i4 = r - m * d4;
+      if (c < PT * cpr && x >= 0) cp_async16(Xst + p * xrow + m * qstride + 4 * i4, reinterpret_cast<const float4*>(P.xsub + x * Px * d) + r);
+    }
+  };
+  const int gi_lines = (L * 4 + 127) / 128, row_lines = (Px * d * 4 + 127) / 128;
+
+  int64_t mine = lane < PT ? item_of(aq.b, g * PT + lane) : -1;
+  if (ST) stage_rows(mine);
+
+  for (; t < t1; ++t) {
+    const int b = aq.b;
+    if (b != staged) {  // (re)stage this query: gq and Q_sub
+      __syncwarp();
+      for (int i = lane; i < L; i += 32) gqs[i] = P.gq[(int64_t)b * L + i];
+      for (int i = lane; i < Pq * d; i += 32) Qs[(i / d) * qstride + (i % d)] = P.qsub[(int64_t)b * Pq * d + i];
+      staged = b;
+    }
     int64_t item[PT];
     bool valid[PT];
 #pragma unroll
     for (int p = 0; p < PT; ++p) {
-      int64_t j = g * PT + p;
-      int64_t x = -1;
-      if (j < P.n_per_query) x = P.cand ? (int64_t)P.cand[(int64_t)b * P.ld + j] : j;
-      valid[p] = (x >= 0 && x < P.N);
+      const int64_t x = __shfl_sync(0xffffffffu, mine, p);
+      valid[p] = x >= 0;
       item[p] = valid[p] ? x : 0;
     }
+    // next work item (warp-uniform)
+    int64_t gn = g + 1;
+    int bn = b;
+    if (gn == groups) {
+      gn = 0;
+      aq.next();
+      bn = aq.b;
+    }
+    const bool more = t + 1 < t1 && bn < P.B;
+    const int64_t mine_n = (more && lane < PT) ? item_of(bn, gn * PT + lane) : -1;
+    if (ST) cp_async_wait_all();
+    __syncwarp();
 
     // ---- 1. logits  l = n*Px + m  (einsum "bnd,xmd->bxnm" then / tau)
     float lg[PT][LL];
 #pragma unroll
-    for (int ll = 0; ll < LL; ++ll) {
-      const int l = lane + 32 * ll;
-      const int n = l / Px, m = l % Px;
-      const float4* q4 = reinterpret_cast<const float4*>(Qs + n * qstride);
+    for (int p = 0; p < PT; ++p) {
 #pragma unroll
-      for (int p = 0; p < PT; ++p) {
-        const float4* x4 = reinterpret_cast<const float4*>(P.xsub + (item[p] * Px + m) * d);
+      for (int ll = 0; ll < LL; ++ll) {
+        const int l = lane + 32 * ll;
+        const int n = l / Px, m = l % Px;
+        const float4* q4 = reinterpret_cast<const float4*>(Qs + n * qstride);
         float s = 0.f;
-        for (int i = 0; i < d / 4; ++i) {
-          float4 a = q4[i], c = __ldg(x4 + i);
-          s = fmaf(a.x, c.x, s);
-          s = fmaf(a.y, c.y, s);
-          s = fmaf(a.z, c.z, s);
-          s = fmaf(a.w, c.w, s);
+        if (ST) {
+          const float4* x4 = reinterpret_cast<const float4*>(Xst + p * xrow + m * qstride);
+#pragma unroll 8
+          for (int i = 0; i < d4; ++i) {
+            const float4 a = q4[i], c = x4[i];
+            s = fmaf(a.x, c.x, s);
+            s = fmaf(a.y, c.y, s);
+            s = fmaf(a.z, c.z, s);
+            s = fmaf(a.w, c.w, s);
+          }
+        } else {
+          const float4* x4 = reinterpret_cast<const float4*>(P.xsub + (item[p] * Px + m) * d);
+          int i = 0;
+          for (; i + 8 <= d4; i += 8) {  // 8 independent 16-byte loads in flight, then the (ordered) FMA chain
+            float4 c[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) c[u] = __ldg(x4 + i + u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 a = q4[i + u];
+              s = fmaf(a.x, c[u].x, s);
+              s = fmaf(a.y, c[u].y, s);
+              s = fmaf(a.z, c[u].z, s);
+              s = fmaf(a.w, c[u].w, s);
+            }
+          }
+          for (; i < d4; ++i) {
+            const float4 a = q4[i], c = __ldg(x4 + i);
+            s = fmaf(a.x, c.x, s);
+            s = fmaf(a.y, c.y, s);
+            s = fmaf(a.z, c.z, s);
+            s = fmaf(a.w, c.w, s);
+          }
         }
         s = s / P.temperature;
         lg[p][ll] = s;
@@ -135,6 +266,19 @@ __global__ void __launch_bounds__(EX_THREADS) exact_scores_kernel(ExactParams P)
       }
     }
     __syncwarp();
+
+    if (more) {  // next work item: start the copy of its X_sub rows (ST) / prefetch them into L2, prefetch its GI rows
+      if (ST) stage_rows(mine_n);
+      const int lines = gi_lines + (ST ? 0 : row_lines);
+      for (int i0 = 0; i0 < PT * lines; i0 += 32) {
+        const int i = i0 + lane;
+        const int p = min(i / lines, PT - 1), ln = i - p * lines;
+        const int64_t x = __shfl_sync(0xffffffffu, mine_n, p);
+        if (i < PT * lines && x >= 0)
+          prefetch_l2(ln < gi_lines ? reinterpret_cast<const char*>(P.gi + x * L) + ln * 128
+                                    : reinterpret_cast<const char*>(P.xsub + x * Px * d) + (ln - gi_lines) * 128);
+      }
+    }
 
     // ---- 2. hidden = silu(W1 l + b1)
     {
@@ -149,7 +293,7 @@ __global__ void __launch_bounds__(EX_THREADS) exact_scores_kernel(ExactParams P)
       for (int l = 0; l < L; ++l) {
         float wv[HH];
 #pragma unroll
-        for (int jj = 0; jj < HH; ++jj) wv[jj] = W1t[l * H + lane + 32 * jj];
+        for (int jj = 0; jj < HH; ++jj) wv[jj] = WS ? W1s[l * H + lane + 32 * jj] : __ldg(P.w1t + l * H + lane + 32 * jj);
         float4 x0 = *reinterpret_cast<const float4*>(logT + l * PT);
         float4 x1 = *reinterpret_cast<const float4*>(logT + l * PT + 4);
         float xv[PT] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
@@ -168,7 +312,12 @@ __global__ void __launch_bounds__(EX_THREADS) exact_scores_kernel(ExactParams P)
     }
     __syncwarp();
 
-    // ---- 3. gate pre-activation  G = gq*gi + (W2 h + b2)
+    // ---- 3. gate pre-activation  G = gq*gi + (W2 h + b2)   (the GI rows are requested first, used in step 4)
+    float giv[PT][LL];
+#pragma unroll
+    for (int p = 0; p < PT; ++p)
+#pragma unroll
+      for (int ll = 0; ll < LL; ++ll) giv[p][ll] = __ldg(P.gi + item[p] * L + lane + 32 * ll);
     float G[PT][LL];
 #pragma unroll
     for (int ll = 0; ll < LL; ++ll) {
@@ -180,7 +329,7 @@ __global__ void __launch_bounds__(EX_THREADS) exact_scores_kernel(ExactParams P)
     for (int j = 0; j < H; ++j) {
       float wv[LL];
 #pragma unroll
-      for (int ll = 0; ll < LL; ++ll) wv[ll] = W2t[j * L + lane + 32 * ll];
+      for (int ll = 0; ll < LL; ++ll) wv[ll] = WS ? W2s[j * L + lane + 32 * ll] : __ldg(P.w2t + j * L + lane + 32 * ll);
       float4 h0 = *reinterpret_cast<const float4*>(hidT + j * PT);
       float4 h1 = *reinterpret_cast<const float4*>(hidT + j * PT + 4);
       float hv[PT] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
@@ -199,8 +348,7 @@ __global__ void __launch_bounds__(EX_THREADS) exact_scores_kernel(ExactParams P)
 #pragma unroll
       for (int ll = 0; ll < LL; ++ll) {
         const int l = lane + 32 * ll;
-        float gi = __ldg(P.gi + item[p] * L + l);
-        float gg = gqs[l] * gi + G[p][ll];
+        float gg = gqs[l] * giv[p][ll] + G[p][ll];
         float w = gg * (1.f / (1.f + expf(-gg)));
         wv[ll] = w;
         mx = fmaxf(mx, w);
@@ -238,29 +386,38 @@ __global__ void __launch_bounds__(EX_THREADS) exact_scores_kernel(ExactParams P)
         P.scores[(int64_t)b * P.ld + j] = valid[p] ? sc : -CUDART_INF_F;
     }
     __syncwarp();
+    g = gn;  // (aq already points at the next work item's query)
+    mine = mine_n;
   }
 }
 
-template <int LL, int HH>
-static int launch_exact_t(const ExactParams& P0, int B, cudaStream_t st) {
-  ExactParams P = P0;
-  const int L = LL * 32, H = HH * 32;
-  size_t fixed = (size_t)(H + 2 * L + P.Pq * (P.d + 4) + EX_WARPS * (L + H) * PT) * sizeof(float);
-  size_t with_w = fixed + (size_t)2 * L * H * sizeof(float);
-  P.w_in_smem = with_w <= 200 * 1024;
-  size_t smem = P.w_in_smem ? with_w : fixed;
-  auto kern = exact_scores_kernel<LL, HH>;
+template <int LL, int HH, int NW, bool WS, bool ST>
+static int launch_exact_nw(const ExactParams& P, int B, size_t smem, cudaStream_t st) {
+  auto kern = exact_scores_kernel<LL, HH, NW, WS, ST>;
   MOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int64_t groups = (P.n_per_query + PT - 1) / PT;
-  int64_t max_x = (groups + EX_WARPS - 1) / EX_WARPS;
-  int64_t want = (148 * 4 + B - 1) / B;
-  int64_t gx = want < 1 ? 1 : want;
-  if (gx > max_x) gx = max_x;
-  if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)B);
-  kern<<<grid, EX_THREADS, smem, st>>>(P);
+  const int64_t groups = (P.n_per_query + PT - 1) / PT;
+  const int64_t work = (int64_t)B * groups;  // upper bound (query_flags may deactivate queries)
+  int64_t blocks = (work + NW - 1) / NW;
+  if (blocks > 148) blocks = 148;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, NW * 32, smem, st>>>(P);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
+}
+
+template <int LL, int HH>
+static int launch_exact_t(const ExactParams& P, int B, cudaStream_t st) {
+  const int L = LL * 32, H = HH * 32;
+  auto bytes = [&](int nw, bool ws, bool stg) {
+    return (size_t)(H + L + nw * (L + P.Pq * (P.d + 4) + (L + H) * PT + (stg ? PT * P.Px * (P.d + 4) : 0)) +
+                    (ws ? 2 * L * H : 0)) * sizeof(float);
+  };
+  const size_t cap = 224 * 1024;
+  constexpr int NW = LL <= 2 ? EXACT_NW_SMALL : 8;
+  if (bytes(NW, true, true) <= cap) return launch_exact_nw<LL, HH, NW, true, true>(P, B, bytes(NW, true, true), st);
+  if (bytes(8, true, false) <= cap) return launch_exact_nw<LL, HH, 8, true, false>(P, B, bytes(8, true, false), st);
+  MOL_CHECK_ARG(bytes(8, false, false) <= cap, "exact kernel: shape needs %zu bytes of shared memory", bytes(8, false, false));
+  return launch_exact_nw<LL, HH, 8, false, false>(P, B, bytes(8, false, false), st);
 }
 
 int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st) {
@@ -291,6 +448,7 @@ int launch_exact_scores(const mol_shape_t& s, const mol_weights_t& w, const mol_
   P.N = ix.num_items;
   P.n_per_query = n_per_query;
   P.ld = ld;
+  P.B = B;
   P.Pq = D.Pq;
   P.Px = D.Px;
   P.d = D.d;
@@ -299,7 +457,6 @@ int launch_exact_scores(const mol_shape_t& s, const mol_weights_t& w, const mol_
   P.temperature = s.temperature;
   P.eps = s.eps;
   P.renorm = s.softmax_renorm;
-  P.w_in_smem = 0;
   MOL_CHECK_ARG(D.H == 128, "exact kernel supports gating_qi_hidden_dim == 128 (got %d)", D.H);
   switch (D.L) {
     case 32: return launch_exact_t<1, 4>(P, B, st);
