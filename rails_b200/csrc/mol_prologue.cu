@@ -12,12 +12,15 @@
 namespace mol {
 
 // ------------------------------------------------------------------------------------------
-// Tiled fp32 GEMM:  C[M,N] = act(A[M,K] W^T + bias),  64x64 tile, 16-deep K slab, 4x4 per thread.
+// Tiled fp32 GEMM:  C[M,N] = act(A[M,K] W^T + bias),  64x64 tile, 64-deep K slab, 4x4 per thread.  The next slab is
+// fetched into registers while the current one is multiplied: the query prologue runs these GEMMs with a handful
+// of blocks (M = B <= 512), where each exposed global-memory round trip costs about a microsecond.
 // ------------------------------------------------------------------------------------------
-constexpr int LT_M = 64, LT_N = 64, LT_K = 16;
+constexpr int LT_M = 64, LT_N = 64, LT_K = 64;
+constexpr int LT_LD = LT_M * LT_K / 256;  // elements of each operand tile a thread fetches per slab
 
 template <int ACT>
-__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A,
+__global__ void __launch_bounds__(256, 2) linear_kernel(const float* __restrict__ A,
                                                      const float* __restrict__ W,
                                                      const float* __restrict__ bias,
                                                      float* __restrict__ C, int64_t M, int N, int K,
@@ -34,15 +37,19 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += LT_K) {
-    // A tile: 64 rows x 16 k; consecutive threads walk k (contiguous in memory).
-    for (int e = tid; e < LT_M * LT_K; e += 256) {
-      int r = e / LT_K, kk = e % LT_K;
-      int64_t m = m0 + r;
-      int k = k0 + kk;
-      As[kk][r] = (m < M && k < K) ? A[m * K + k] : 0.f;
+  float ra[LT_LD], rw[LT_LD];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < LT_LD; ++u) {  // A tile: consecutive threads walk k (contiguous in memory)
+      const int e = tid + u * 256;
+      const int r = e / LT_K, kk = e % LT_K;
+      const int64_t m = m0 + r;
+      const int k = k0 + kk;
+      ra[u] = (m < M && k < K) ? __ldg(A + m * K + k) : 0.f;
     }
-    for (int e = tid; e < LT_N * LT_K; e += 256) {
+#pragma unroll
+    for (int u = 0; u < LT_LD; ++u) {
+      const int e = tid + u * 256;
       int r, kk;
       if (w_sk == 1) {  // (n,k) with k contiguous
         r = e / LT_K;
@@ -51,11 +58,28 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A
         kk = e / LT_N;
         r = e % LT_N;
       }
-      int n = n0 + r, k = k0 + kk;
-      Ws[kk][r] = (n < N && k < K) ? W[n * w_sn + k * w_sk] : 0.f;
+      const int n = n0 + r, k = k0 + kk;
+      rw[u] = (n < N && k < K) ? __ldg(W + n * w_sn + k * w_sk) : 0.f;
     }
-    __syncthreads();
+  };
+  auto stash = [&]() {
 #pragma unroll
+    for (int u = 0; u < LT_LD; ++u) {
+      const int e = tid + u * 256;
+      As[e % LT_K][e / LT_K] = ra[u];
+      if (w_sk == 1)
+        Ws[e % LT_K][e / LT_K] = rw[u];
+      else
+        Ws[e / LT_N][e % LT_N] = rw[u];
+    }
+  };
+
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += LT_K) {
+    stash();
+    __syncthreads();
+    if (k0 + LT_K < K) fetch(k0 + LT_K);
+#pragma unroll 8
     for (int kk = 0; kk < LT_K; ++kk) {
       float a[4], b[4];
 #pragma unroll
