@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(256, 2) linear_kernel(const float* __restrict_
                                                      const float* __restrict__ bias,
                                                      float* __restrict__ C, int64_t M, int N, int K,
                                                      int64_t w_sn, int64_t w_sk) {
-  __shared__ float As[LT_K][LT_M + 4];
-  __shared__ float Ws[LT_K][LT_N + 4];
+  __shared__ __align__(16) float As[LT_K][LT_M + 4];
+  __shared__ __align__(16) float Ws[LT_K][LT_N + 4];
   const int tid = threadIdx.x;
   const int64_t m0 = (int64_t)blockIdx.x * LT_M;
   const int n0 = blockIdx.y * LT_N;
@@ -81,11 +81,9 @@ __global__ void __launch_bounds__(256, 2) linear_kernel(const float* __restrict_
     if (k0 + LT_K < K) fetch(k0 + LT_K);
 #pragma unroll 8
     for (int kk = 0; kk < LT_K; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Ws[kk][tx * 4 + j];
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -166,10 +164,67 @@ __global__ void l2norm_groups_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
+// d / 4 = G lanes (a power of two <= 32) per d-vector, one float4 per lane, UNR vectors in flight per lane group:
+// the index build normalises N * P_X vectors (HBM-bound: 4 B read + 6 B written per element).
+template <int G, int UNR>
+__global__ void __launch_bounds__(256) l2norm_groups_vec_kernel(const float4* __restrict__ in, float4* __restrict__ out_f32,
+                                                                uint2* __restrict__ out_half, int64_t n_vec, float eps) {
+  const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;  // lane group index
+  const int gl = threadIdx.x % G;
+  const int64_t n_slots = (int64_t)gridDim.x * blockDim.x / G;
+  const int64_t warp_slot = slot - (threadIdx.x % 32) / G;  // first lane group of this warp: warp-uniform loop bound
+  for (int64_t w0 = warp_slot, v0 = slot; w0 < n_vec; w0 += n_slots * UNR, v0 += n_slots * UNR) {
+    float4 x[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t v = v0 + (int64_t)u * n_slots;
+      x[u] = v < n_vec ? __ldg(in + v * G + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t v = v0 + (int64_t)u * n_slots;
+      float ss = x[u].x * x[u].x;
+      ss = fmaf(x[u].y, x[u].y, ss);
+      ss = fmaf(x[u].z, x[u].z, ss);
+      ss = fmaf(x[u].w, x[u].w, ss);
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float nrm = fmaxf(sqrtf(ss), eps);
+      const float4 y = make_float4(x[u].x / nrm, x[u].y / nrm, x[u].z / nrm, x[u].w / nrm);
+      if (v < n_vec) {
+        if (out_f32) out_f32[v * G + gl] = y;
+        if (out_half) {  // |y| <= 1: always representable
+          const __half2 lo = __floats2half2_rn(y.x, y.y), hi = __floats2half2_rn(y.z, y.w);
+          out_half[v * G + gl] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
+      }
+    }
+  }
+}
+
+template <int G>
+static void launch_l2norm_vec(const float* in, float* out_f32, __half* out_half, int64_t n_vec, float eps, cudaStream_t st) {
+  constexpr int UNR = 4;
+  const int64_t slots_per_block = 256 / G;
+  int64_t blocks = (n_vec + slots_per_block * UNR - 1) / (slots_per_block * UNR);
+  if (blocks < 1) blocks = 1;
+  l2norm_groups_vec_kernel<G, UNR><<<(unsigned)blocks, 256, 0, st>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out_f32), reinterpret_cast<uint2*>(out_half), n_vec, eps);
+}
+
 int launch_l2norm_groups(const float* in, float* out_f32, __half* out_half, int64_t rows,
                          int groups, int d, float eps, cudaStream_t st) {
   int64_t n_vec = rows * groups;
   if (n_vec == 0) return MOL_OK;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out_f32)) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(out_half) & 7) == 0;
+  if (aligned && (d == 32 || d == 64 || d == 128) && n_vec >= 4096) {
+    if (d == 32) launch_l2norm_vec<8>(in, out_f32, out_half, n_vec, eps, st);
+    else if (d == 64) launch_l2norm_vec<16>(in, out_f32, out_half, n_vec, eps, st);
+    else launch_l2norm_vec<32>(in, out_f32, out_half, n_vec, eps, st);
+    MOL_LAUNCH_CHECK();
+    return MOL_OK;
+  }
   int64_t threads = n_vec * 32;
   l2norm_groups_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, out_f32, out_half,
                                                                           n_vec, d, eps);
