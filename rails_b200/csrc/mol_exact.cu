@@ -216,54 +216,70 @@ __global__ void __launch_bounds__(NW * 32) exact_scores_kernel(ExactParams P) {
     if (ST) cp_async_wait_all();
     __syncwarp();
 
-    // ---- 1. logits  l = n*Px + m  (einsum "bnd,xmd->bxnm" then / tau)
+    // ---- 1. logits  l = n*Px + m  (einsum "bnd,xmd->bxnm" then / tau).  k runs outermost with the PT*LL dot products
+    //      as independent chains (each still accumulates in k order); when P_X divides 32 the item group m of a
+    //      lane is the same for all its logits, so one X_sub fragment serves them all.
     float lg[PT][LL];
+    {
+      float s[PT][LL];
 #pragma unroll
-    for (int p = 0; p < PT; ++p) {
+      for (int p = 0; p < PT; ++p)
 #pragma unroll
-      for (int ll = 0; ll < LL; ++ll) {
-        const int l = lane + 32 * ll;
-        const int n = l / Px, m = l % Px;
-        const float4* q4 = reinterpret_cast<const float4*>(Qs + n * qstride);
-        float s = 0.f;
-        if (ST) {
-          const float4* x4 = reinterpret_cast<const float4*>(Xst + p * xrow + m * qstride);
-#pragma unroll 8
+        for (int ll = 0; ll < LL; ++ll) s[p][ll] = 0.f;
+      const bool same_m = (32 % Px) == 0;
+      const int m0 = lane % Px;
+      const float4* qrow[LL];
+#pragma unroll
+      for (int ll = 0; ll < LL; ++ll) qrow[ll] = reinterpret_cast<const float4*>(Qs + ((lane + 32 * ll) / Px) * qstride);
+      if (ST && same_m) {
+        const float4* xbase = reinterpret_cast<const float4*>(Xst + m0 * qstride);
+#pragma unroll 2
+        for (int i = 0; i < d4; ++i) {
+          float4 a[LL], c[PT];
+#pragma unroll
+          for (int ll = 0; ll < LL; ++ll) a[ll] = qrow[ll][i];
+#pragma unroll
+          for (int p = 0; p < PT; ++p) c[p] = xbase[p * (xrow / 4) + i];
+#pragma unroll
+          for (int p = 0; p < PT; ++p)
+#pragma unroll
+            for (int ll = 0; ll < LL; ++ll) {
+              s[p][ll] = fmaf(a[ll].x, c[p].x, s[p][ll]);
+              s[p][ll] = fmaf(a[ll].y, c[p].y, s[p][ll]);
+              s[p][ll] = fmaf(a[ll].z, c[p].z, s[p][ll]);
+              s[p][ll] = fmaf(a[ll].w, c[p].w, s[p][ll]);
+            }
+        }
+      } else {
+#pragma unroll
+        for (int ll = 0; ll < LL; ++ll) {
+          const int m = (lane + 32 * ll) % Px;
+#pragma unroll 2
           for (int i = 0; i < d4; ++i) {
-            const float4 a = q4[i], c = x4[i];
-            s = fmaf(a.x, c.x, s);
-            s = fmaf(a.y, c.y, s);
-            s = fmaf(a.z, c.z, s);
-            s = fmaf(a.w, c.w, s);
-          }
-        } else {
-          const float4* x4 = reinterpret_cast<const float4*>(P.xsub + (item[p] * Px + m) * d);
-          int i = 0;
-          for (; i + 8 <= d4; i += 8) {  // 8 independent 16-byte loads in flight, then the (ordered) FMA chain
-            float4 c[8];
+            const float4 a = qrow[ll][i];
+            float4 c[PT];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) c[u] = __ldg(x4 + i + u);
+            for (int p = 0; p < PT; ++p)
+              c[p] = ST ? reinterpret_cast<const float4*>(Xst + p * xrow + m * qstride)[i]
+                        : __ldg(reinterpret_cast<const float4*>(P.xsub + (item[p] * Px + m) * d) + i);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float4 a = q4[i + u];
-              s = fmaf(a.x, c[u].x, s);
-              s = fmaf(a.y, c[u].y, s);
-              s = fmaf(a.z, c[u].z, s);
-              s = fmaf(a.w, c[u].w, s);
+            for (int p = 0; p < PT; ++p) {
+              s[p][ll] = fmaf(a.x, c[p].x, s[p][ll]);
+              s[p][ll] = fmaf(a.y, c[p].y, s[p][ll]);
+              s[p][ll] = fmaf(a.z, c[p].z, s[p][ll]);
+              s[p][ll] = fmaf(a.w, c[p].w, s[p][ll]);
             }
           }
-          for (; i < d4; ++i) {
-            const float4 a = q4[i], c = __ldg(x4 + i);
-            s = fmaf(a.x, c.x, s);
-            s = fmaf(a.y, c.y, s);
-            s = fmaf(a.z, c.z, s);
-            s = fmaf(a.w, c.w, s);
-          }
         }
-        s = s / P.temperature;
-        lg[p][ll] = s;
-        logT[l * PT + p] = s;
       }
+#pragma unroll
+      for (int p = 0; p < PT; ++p)
+#pragma unroll
+        for (int ll = 0; ll < LL; ++ll) {
+          const float v = s[p][ll] / P.temperature;
+          lg[p][ll] = v;
+          logT[(lane + 32 * ll) * PT + p] = v;
+        }
     }
     __syncwarp();
 
@@ -280,33 +296,38 @@ __global__ void __launch_bounds__(NW * 32) exact_scores_kernel(ExactParams P) {
       }
     }
 
-    // ---- 2. hidden = silu(W1 l + b1)
+    // ---- 2. hidden = silu(W1 l + b1).  The accumulators of two items share one packed fma.rn.f32x2 (same
+    //      per-element rounding as fmaf, half the issue slots).
     {
-      float acc[PT][HH];
+      float2 acc[PT / 2][HH];
 #pragma unroll
       for (int jj = 0; jj < HH; ++jj) {
         float bv = b1s[lane + 32 * jj];
 #pragma unroll
-        for (int p = 0; p < PT; ++p) acc[p][jj] = bv;
+        for (int q = 0; q < PT / 2; ++q) acc[q][jj] = make_float2(bv, bv);
       }
 #pragma unroll 4
       for (int l = 0; l < L; ++l) {
-        float wv[HH];
+        float2 wv[HH];
 #pragma unroll
-        for (int jj = 0; jj < HH; ++jj) wv[jj] = WS ? W1s[l * H + lane + 32 * jj] : __ldg(P.w1t + l * H + lane + 32 * jj);
+        for (int jj = 0; jj < HH; ++jj) {
+          const float w = WS ? W1s[l * H + lane + 32 * jj] : __ldg(P.w1t + l * H + lane + 32 * jj);
+          wv[jj] = make_float2(w, w);
+        }
         float4 x0 = *reinterpret_cast<const float4*>(logT + l * PT);
         float4 x1 = *reinterpret_cast<const float4*>(logT + l * PT + 4);
-        float xv[PT] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        const float2 xv[PT / 2] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y),
+                                   make_float2(x1.z, x1.w)};
 #pragma unroll
-        for (int p = 0; p < PT; ++p)
+        for (int q = 0; q < PT / 2; ++q)
 #pragma unroll
-          for (int jj = 0; jj < HH; ++jj) acc[p][jj] = fmaf(xv[p], wv[jj], acc[p][jj]);
+          for (int jj = 0; jj < HH; ++jj) acc[q][jj] = __ffma2_rn(xv[q], wv[jj], acc[q][jj]);
       }
 #pragma unroll
       for (int jj = 0; jj < HH; ++jj)
 #pragma unroll
         for (int p = 0; p < PT; ++p) {
-          float a = acc[p][jj];
+          float a = (p & 1) ? acc[p / 2][jj].y : acc[p / 2][jj].x;
           hidT[(lane + 32 * jj) * PT + p] = a / (1.f + expf(-a));
         }
     }
@@ -318,72 +339,110 @@ __global__ void __launch_bounds__(NW * 32) exact_scores_kernel(ExactParams P) {
     for (int p = 0; p < PT; ++p)
 #pragma unroll
       for (int ll = 0; ll < LL; ++ll) giv[p][ll] = __ldg(P.gi + item[p] * L + lane + 32 * ll);
-    float G[PT][LL];
+    float2 G2[PT / 2][LL];
 #pragma unroll
     for (int ll = 0; ll < LL; ++ll) {
       float bv = b2s[lane + 32 * ll];
 #pragma unroll
-      for (int p = 0; p < PT; ++p) G[p][ll] = bv;
+      for (int q = 0; q < PT / 2; ++q) G2[q][ll] = make_float2(bv, bv);
     }
 #pragma unroll 4
     for (int j = 0; j < H; ++j) {
-      float wv[LL];
+      float2 wv[LL];
 #pragma unroll
-      for (int ll = 0; ll < LL; ++ll) wv[ll] = WS ? W2s[j * L + lane + 32 * ll] : __ldg(P.w2t + j * L + lane + 32 * ll);
+      for (int ll = 0; ll < LL; ++ll) {
+        const float w = WS ? W2s[j * L + lane + 32 * ll] : __ldg(P.w2t + j * L + lane + 32 * ll);
+        wv[ll] = make_float2(w, w);
+      }
       float4 h0 = *reinterpret_cast<const float4*>(hidT + j * PT);
       float4 h1 = *reinterpret_cast<const float4*>(hidT + j * PT + 4);
-      float hv[PT] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+      const float2 hv[PT / 2] = {make_float2(h0.x, h0.y), make_float2(h0.z, h0.w), make_float2(h1.x, h1.y),
+                                 make_float2(h1.z, h1.w)};
 #pragma unroll
-      for (int p = 0; p < PT; ++p)
+      for (int q = 0; q < PT / 2; ++q)
 #pragma unroll
-        for (int ll = 0; ll < LL; ++ll) G[p][ll] = fmaf(hv[p], wv[ll], G[p][ll]);
+        for (int ll = 0; ll < LL; ++ll) G2[q][ll] = __ffma2_rn(hv[q], wv[ll], G2[q][ll]);
     }
+    float G[PT][LL];
+#pragma unroll
+    for (int p = 0; p < PT; ++p)
+#pragma unroll
+      for (int ll = 0; ll < LL; ++ll) G[p][ll] = (p & 1) ? G2[p / 2][ll].y : G2[p / 2][ll].x;
     __syncwarp();
 
-    // ---- 4. w = G*sigmoid(G); softmax over L; renorm; weighted sum
+    // ---- 4. w = G*sigmoid(G); softmax over L; renorm; weighted sum.  Stage-major over the PT items, so the PT
+    //      shuffle / division chains of a stage are independent and overlap (same per-item arithmetic).
+    {
+      float wv[PT][LL], r0[PT], r1[PT];
 #pragma unroll
-    for (int p = 0; p < PT; ++p) {
-      float wv[LL];
-      float mx = -CUDART_INF_F;
+      for (int p = 0; p < PT; ++p) {
+        float mx = -CUDART_INF_F;
 #pragma unroll
-      for (int ll = 0; ll < LL; ++ll) {
-        const int l = lane + 32 * ll;
-        float gg = gqs[l] * giv[p][ll] + G[p][ll];
-        float w = gg * (1.f / (1.f + expf(-gg)));
-        wv[ll] = w;
-        mx = fmaxf(mx, w);
+        for (int ll = 0; ll < LL; ++ll) {
+          const int l = lane + 32 * ll;
+          float gg = gqs[l] * giv[p][ll] + G[p][ll];
+          float w = gg * (1.f / (1.f + expf(-gg)));
+          wv[p][ll] = w;
+          mx = fmaxf(mx, w);
+        }
+        r0[p] = mx;
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float sum = 0.f;
+      for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int ll = 0; ll < LL; ++ll) {
-        wv[ll] = expf(wv[ll] - mx);
-        sum += wv[ll];
+        for (int p = 0; p < PT; ++p) r0[p] = fmaxf(r0[p], __shfl_xor_sync(0xffffffffu, r0[p], o));
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        float sum = 0.f;
+#pragma unroll
+        for (int ll = 0; ll < LL; ++ll) {
+          wv[p][ll] = expf(wv[p][ll] - r0[p]);
+          sum += wv[p][ll];
+        }
+        r1[p] = sum;
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      float psum = 0.f;
+      for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int ll = 0; ll < LL; ++ll) {
-        wv[ll] = wv[ll] / sum;
-        psum += wv[ll];
+        for (int p = 0; p < PT; ++p) r1[p] += __shfl_xor_sync(0xffffffffu, r1[p], o);
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        float psum = 0.f;
+#pragma unroll
+        for (int ll = 0; ll < LL; ++ll) {
+          wv[p][ll] = wv[p][ll] / r1[p];
+          psum += wv[p][ll];
+        }
+        r0[p] = psum;
       }
       if (P.renorm) {  // similarity_fn.py:43-45 (dropout is identity in eval, the renorm still runs)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
-        float den = fmaxf(psum, P.eps);
+        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int ll = 0; ll < LL; ++ll) wv[ll] = wv[ll] / den;
+          for (int p = 0; p < PT; ++p) r0[p] += __shfl_xor_sync(0xffffffffu, r0[p], o);
+#pragma unroll
+        for (int p = 0; p < PT; ++p) {
+          const float den = fmaxf(r0[p], P.eps);
+#pragma unroll
+          for (int ll = 0; ll < LL; ++ll) wv[p][ll] = wv[p][ll] / den;
+        }
       }
-      float sc = 0.f;
 #pragma unroll
-      for (int ll = 0; ll < LL; ++ll) sc = fmaf(wv[ll], lg[p][ll], sc);
+      for (int p = 0; p < PT; ++p) {
+        float sc = 0.f;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
-      int64_t j = g * PT + p;
-      if (lane == 0 && j < P.n_per_query)
-        P.scores[(int64_t)b * P.ld + j] = valid[p] ? sc : -CUDART_INF_F;
+        for (int ll = 0; ll < LL; ++ll) sc = fmaf(wv[p][ll], lg[p][ll], sc);
+        r1[p] = sc;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int p = 0; p < PT; ++p) r1[p] += __shfl_xor_sync(0xffffffffu, r1[p], o);
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        const int64_t j = g * PT + p;
+        if (lane == 0 && j < P.n_per_query) P.scores[(int64_t)b * P.ld + j] = valid[p] ? r1[p] : -CUDART_INF_F;
+      }
     }
     __syncwarp();
     g = gn;  // (aq already points at the next work item's query)
