@@ -135,3 +135,33 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_get_top_k_module_names_match_the_reference():
+    """indexing/utils_rails.py:25-233 of the reference: same method names -> same classes / constructor arguments."""
+    import types
+
+    import pytest
+    import torch
+
+    from rails_b200.indexing import mol_top_k as M
+    from rails_b200.indexing.mips_top_k import MIPSBruteForceTopK
+    from rails_b200.indexing.utils_rails import get_top_k_module
+    from tests.helpers import CFG_8x8x32, build_module
+
+    mol, _ = build_module(CFG_8x8x32, None, "cpu")
+    model = types.SimpleNamespace(_ndp_module=mol)
+    items, ids = torch.randn(1, 300, 64), torch.arange(1, 301).unsqueeze(0)
+    assert isinstance(get_top_k_module("MIPSBruteForceTopK", model, items, ids), MIPSBruteForceTopK)
+    assert isinstance(get_top_k_module("MoLBruteForceTopK", model, items, ids), M.MoLBruteForceTopK)
+    t = get_top_k_module("MoLNaiveTopK25", model, items, ids)
+    assert isinstance(t, M.MoLNaiveTopK) and t._k_per_group == 25 and t.mol_module is mol
+    t = get_top_k_module("MoLAvgTopK2500", model, items, ids)
+    assert isinstance(t, M.MoLAvgTopK) and t._avg_top_k == 2500
+    t = get_top_k_module("MoLCombTopK50_1000", model, items, ids)
+    assert isinstance(t, M.MoLCombTopK) and (t._k_per_group, t._avg_top_k) == (50, 1000)
+    for bad in ("MoLNaiveTopK7", "MoLAvgTopK123", "MoLCombTopK5_1000", "FaissTopK", ""):
+        with pytest.raises(ValueError, match="Invalid top-k method"):
+            get_top_k_module(bad, model, items, ids)
+    with pytest.raises(NotImplementedError):
+        get_top_k_module("MoLNaiveFaissTopK5", model, items, ids)
