@@ -357,8 +357,8 @@ __global__ void probe_tmem_kernel(int which, int iters, float* sink, long long* 
 // (M = 128, K = 16, N = n) back to back, then commits.  mode 0: SS (A, B from smem), 1: TS (A from TMEM).
 // out: cycles[0] = issue loop, cycles[1] = until the commit's mbarrier fires.
 // ------------------------------------------------------------------------------------------------
-template <int N>
-__global__ void probe_mma_rate_kernel(int mode, int iters, long long* cycles) {
+template <int N, int mode>
+__global__ void probe_mma_rate_kernel(int iters, long long* cycles) {
   extern __shared__ unsigned char smem_raw2[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -380,11 +380,32 @@ __global__ void probe_mma_rate_kernel(int mode, int iters, long long* cycles) {
     const uint32_t sA = smem_u32(smem), sB = smem_u32(smem + 16384);
     const uint64_t da = make_smem_desc(sA, 16, 1024, 2);
     const uint64_t db = make_smem_desc(sB, 128, 256, 0);
+    const uint64_t db2 = make_smem_desc(sB + 256 * 16, 128, 256, 0);
     long long t0 = clock64();
     if (elect_one_sync()) {
-      for (int i = 0; i < iters; ++i) {
-        if (mode == 0) umma_ss(tmem + 256, da, db, idesc, 1u);
-        else umma_ts(tmem + 256, tmem, db, idesc, 1u);
+      for (int i = 0; i < iters; i += 4) {  // branch-free body: `mode` is a template parameter
+        if constexpr (mode == 0) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) umma_ss(tmem + 256, da, db, idesc, 1u);
+        } else if constexpr (mode == 1) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) umma_ts(tmem + 256, tmem, db, idesc, 1u);
+        } else if constexpr (mode == 2) {  // pairs sharing A through the collector: fill, then lastuse into another accumulator
+          umma_ss_coll<1>(tmem + 256, da, db, idesc, 1u);
+          umma_ss_coll<3>(tmem + 256 + N, da, db2, idesc, 1u);
+          umma_ss_coll<1>(tmem + 256, da, db, idesc, 1u);
+          umma_ss_coll<3>(tmem + 256 + N, da, db2, idesc, 1u);
+        } else if constexpr (mode == 3) {  // the same pairs without the hint (two accumulators, same A)
+          umma_ss(tmem + 256, da, db, idesc, 1u);
+          umma_ss(tmem + 256 + N, da, db2, idesc, 1u);
+          umma_ss(tmem + 256, da, db, idesc, 1u);
+          umma_ss(tmem + 256 + N, da, db2, idesc, 1u);
+        } else {  // groups of four: fill, use, use, lastuse
+          umma_ss_coll<1>(tmem + 256, da, db, idesc, 1u);
+          umma_ss_coll<2>(tmem + 256 + N, da, db2, idesc, 1u);
+          umma_ss_coll<2>(tmem + 256, da, db, idesc, 1u);
+          umma_ss_coll<3>(tmem + 256 + N, da, db2, idesc, 1u);
+        }
       }
       umma_commit(&bar);
     }
@@ -495,13 +516,19 @@ int probe_tmem(int which, int iters, int threads, int blocks, float* sink, long 
 
 int probe_mma_rate(int n, int mode, int iters, int blocks, long long* cycles) {
   size_t smem = 16384 + 256 * 32 + 2048;
-#define RUNR(NN)                                                                                             \
-  {                                                                                                          \
-    cudaFuncSetAttribute(probe_mma_rate_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    probe_mma_rate_kernel<NN><<<blocks, 128, smem>>>(mode, iters, cycles);                                   \
+#define RUNM(NN, MM)                                                                                             \
+  {                                                                                                              \
+    cudaFuncSetAttribute(probe_mma_rate_kernel<NN, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    probe_mma_rate_kernel<NN, MM><<<blocks, 128, smem>>>(iters, cycles);                                         \
+  }
+#define RUNR(NN)                                                                                                  \
+  {                                                                                                               \
+    if (mode == 0) RUNM(NN, 0) else if (mode == 1) RUNM(NN, 1) else if (mode == 2) RUNM(NN, 2)                    \
+    else if (mode == 3) RUNM(NN, 3) else RUNM(NN, 4)                                                              \
   }
   if (n == 16) RUNR(16) else if (n == 32) RUNR(32) else if (n == 64) RUNR(64) else if (n == 128) RUNR(128) else if (n == 256) RUNR(256) else return -1;
 #undef RUNR
+#undef RUNM
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     fprintf(stderr, "probe_mma_rate: %s\n", cudaGetErrorString(e));

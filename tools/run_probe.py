@@ -108,8 +108,8 @@ def tmem():
 def mma_rate():
     cyc = torch.zeros(2, dtype=torch.int64, device="cuda")
     iters = 256
-    for mode, mname in ((0, "SS"), (1, "TS")):
-        for n in (16, 32, 64, 128, 256):
+    for mode, mname in ((0, "SS"), (1, "TS"), (2, "SS collector fill/lastuse pairs"), (3, "SS pairs, no hint"), (4, "SS collector fill/use/use/lastuse")):
+        for n in (16, 32, 64, 128, 256) if mode < 2 else (16, 32):
             lib.probe_mma_rate(n, mode, 8, 148, ptr(cyc))
             rc = lib.probe_mma_rate(n, mode, iters, 148, ptr(cyc))
             c = cyc.tolist()
