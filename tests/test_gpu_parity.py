@@ -89,6 +89,27 @@ def test_top_k_matches_oracle_seeded(cfg, N, B, k, seed, mode):
     assert r["ok"] == 1.0, r
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_duplicate_items_exact_score_collisions(mode):
+    """Collisions: every embedding appears three times under different ids, so each score is an exact 3-way tie
+    (the cut at k falls inside a tie group).  torch.topk leaves the order inside a tie unspecified; the tie-aware
+    comparator accepts any member, but ids must not repeat and every returned score must be that item's score."""
+    cfg = CFG_8x8x32
+    base, B, k = 4000, 7, 100
+    mol, _ = build_module(cfg, None, DEV, seed=9)
+    items, _, q, _ = synthetic_inputs(cfg, base, B, 9, DEV)
+    items = items.repeat(3, 1)
+    ids = torch.randperm(3 * base, generator=torch.Generator().manual_seed(9)).to(DEV) + 1
+    sd = {k_: v.detach().cpu() for k_, v in mol.state_dict().items()}
+    s, got = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=mode)(q, k=k)
+    _, _, all_scores = O.brute_force_top_k(cfg, sd, q.cpu(), items.cpu(), ids.cpu(), k)
+    r = O.compare_top_k(s, got, all_scores, ids.cpu(), k, SCORE_TOL, TIE_TOL)
+    assert r["ok"] == 1.0, r
+    # the three copies of one embedding get bit-identical scores from the rescoring kernel
+    srt = s.cpu()
+    assert int((srt[:, :-1] == srt[:, 1:]).sum()) >= B * (k // 3) * 2 - B * 2
+
+
 def test_k_out_of_range_raises_runtime_error_like_torch_topk():
     g = load_golden("edge_tiny")
     mol, _ = build_module(g["cfg"], g["sd"], DEV)
