@@ -112,6 +112,7 @@ def build_variant(name: str, defs) -> str:
         objs = list(ex.map(one, SOURCES))
     target = os.path.join(OUT_DIR, f"libmol_b200_{name}.so")
     _link(objs, target)
+    shutil.rmtree(odir, ignore_errors=True)  # the objects are not needed again (and would travel with every gpurun snapshot)
     return target
 
 

@@ -60,15 +60,43 @@ constexpr float kGateClamp = 40.f;  // clamp of the half gate pre-activation u (
 #endif
 constexpr int kEx2EmuOf4 = MOL_EX2_EMU_OF4;
 #ifndef MOL_E2_POLY_MASK
-#define MOL_E2_POLY_MASK 0x00
+#define MOL_E2_POLY_MASK 0x0E
 #endif
 // bit c set: chunk c (16 hidden units) of E2 takes tanh from an fp32 odd polynomial on the FMA pipe instead of MUFU.TANH
 constexpr unsigned kE2PolyMask = MOL_E2_POLY_MASK;
-// tanh(u) ~ c * Q(c^2), c = clamp(u, +-3.5), |error| <= 1.9e-3 (minimax fit, tools/fit notes in DESIGN.md)
+// finer control: bit (8 * c + j) set = pair j (two hidden units) of chunk c; defaults to whole chunks of MOL_E2_POLY_MASK
+#ifdef MOL_E2_POLY_MASK64
+constexpr unsigned long long kE2Poly64 = MOL_E2_POLY_MASK64;
+#else
+constexpr unsigned long long expand_chunk_mask(unsigned m) {
+  unsigned long long r = 0;
+  for (int c = 0; c < 8; ++c)
+    if ((m >> c) & 1u) r |= 0xffull << (8 * c);
+  return r;
+}
+constexpr unsigned long long kE2Poly64 = expand_chunk_mask(kE2PolyMask);
+#endif
+#ifndef MOL_E3_POLY_OF4
+#define MOL_E3_POLY_OF4 0
+#endif
+// of every 4 logit pairs of E3, how many take tanh from the polynomial instead of MUFU.TANH
+constexpr int kE3PolyOf4 = MOL_E3_POLY_OF4;
+// tanh(u) ~ c * Q(c^2), c = clamp(u, +-kTanhC) (weighted least-squares minimax fits, fp32 Horner):
+//   MOL_E2_POLY_DEG 6: clamp 3.5,  |error| <= 1.9e-3;   8: clamp 3.75, |error| <= 6.3e-4 (MUFU.TANH.F16 itself: ~5e-4)
+#ifndef MOL_E2_POLY_DEG
+#define MOL_E2_POLY_DEG 8
+#endif
+#if MOL_E2_POLY_DEG == 6
 constexpr float kTanhC = 3.5f;
 constexpr float kT0 = 0.9905173778533936f, kT1 = -0.29184621572494507f, kT2 = 0.07649415731430054f,
                 kT3 = -0.013051184825599194f, kT4 = 0.0013143233954906464f, kT5 = -7.031815766822547e-05f,
-                kT6 = 1.5339735455199843e-06f;  // of every 4 logit pairs, how many take 2^x on the FMA pipe instead of MUFU.EX2
+                kT6 = 1.5339735455199843e-06f, kT7 = 0.f, kT8 = 0.f;
+#else
+constexpr float kTanhC = 3.75f;
+constexpr float kT0 = 0.996860146522522f, kT1 = -0.3149697482585907f, kT2 = 0.10022653639316559f,
+                kT3 = -0.023737963289022446f, kT4 = 0.003820218378677964f, kT5 = -0.0003979474422521889f,
+                kT6 = 2.547265285102185e-05f, kT7 = -9.067708219845372e-07f, kT8 = 1.3707315282829313e-08f;
+#endif
 
 // TMEM column map of one slot (256 columns)
 constexpr uint32_t kColLog = 0;     // LOG fp32 [0, L); A2 fp16 aliases [0, L/2) + ones [L/2, L/2 + 8)
@@ -462,15 +490,21 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tc_fence_after();
       if (warp == 4) TR(1, 1, cnt);
       uint32_t va[16], vb[16];
-      auto act = [&](const uint32_t* v, uint32_t col, bool poly) __attribute__((always_inline)) {
-        uint32_t hk[8];
-        if (poly) {
+      auto act = [&](const uint32_t* v, uint32_t col, unsigned poly) __attribute__((always_inline)) {
+        uint32_t hk[8];  // bit j2 of `poly`: pair j2 of this chunk takes tanh from the polynomial (FMA pipe), else MUFU.TANH
 #pragma unroll
-          for (int j2 = 0; j2 < 8; ++j2) {
+        for (int j2 = 0; j2 < 8; ++j2) {
+          if ((poly >> j2) & 1u) {
             const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
             const float2 c = make_float2(clamp_sym(u.x, kTanhC), clamp_sym(u.y, kTanhC));
             const float2 s2 = __fmul2_rn(c, c);
+#if MOL_E2_POLY_DEG == 6
             float2 p = __ffma2_rn(make_float2(kT6, kT6), s2, make_float2(kT5, kT5));
+#else
+            float2 p = __ffma2_rn(make_float2(kT8, kT8), s2, make_float2(kT7, kT7));
+            p = __ffma2_rn(p, s2, make_float2(kT6, kT6));
+            p = __ffma2_rn(p, s2, make_float2(kT5, kT5));
+#endif
             p = __ffma2_rn(p, s2, make_float2(kT4, kT4));
             p = __ffma2_rn(p, s2, make_float2(kT3, kT3));
             p = __ffma2_rn(p, s2, make_float2(kT2, kT2));
@@ -479,10 +513,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const float2 t = __fmul2_rn(c, p);
             const float2 h = __ffma2_rn(u, t, u);
             hk[j2] = pack_f16x2(h.x, h.y);
-          }
-        } else {
-#pragma unroll
-          for (int j2 = 0; j2 < 8; ++j2) {
+          } else {
             const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
 #ifdef MOL_ABLATE_E2
             hk[j2] = fma_f16x2(u2, u2, u2);
@@ -500,10 +531,10 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int c = 0; c < 8; c += 2) {
         tmem_ld_wait_bind16(va);
         tmem_ld_x16(base + kColHid + 16 * (c + 1), vb);
-        act(va, kColHid + 8 * c, (kE2PolyMask >> c) & 1u);
+        act(va, kColHid + 8 * c, (unsigned)((kE2Poly64 >> (8 * c)) & 0xffull));
         tmem_ld_wait_bind16(vb);
         if (c + 2 < 8) tmem_ld_x16(base + kColHid + 16 * (c + 2), va);
-        act(vb, kColHid + 8 * (c + 1), (kE2PolyMask >> (c + 1)) & 1u);
+        act(vb, kColHid + 8 * (c + 1), (unsigned)((kE2Poly64 >> (8 * (c + 1))) & 0xffull));
         if (c == 2) {  // first half of A3 (k < 64) is in TMEM: the issuer may start G3
           tmem_st_wait();
           tc_fence_before();
@@ -627,7 +658,22 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #ifdef MOL_ABLATE_E3
           const float2 t = u;
 #else
-          const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+          float2 t;
+          if ((j2 & 3) >= 4 - kE3PolyOf4) {  // tanh of this logit pair on the FMA pipe (same polynomial as E2)
+            const float2 c = make_float2(clamp_sym(u.x, kTanhC), clamp_sym(u.y, kTanhC));
+            const float2 s2 = __fmul2_rn(c, c);
+            float2 p = __ffma2_rn(make_float2(kT8, kT8), s2, make_float2(kT7, kT7));
+            p = __ffma2_rn(p, s2, make_float2(kT6, kT6));
+            p = __ffma2_rn(p, s2, make_float2(kT5, kT5));
+            p = __ffma2_rn(p, s2, make_float2(kT4, kT4));
+            p = __ffma2_rn(p, s2, make_float2(kT3, kT3));
+            p = __ffma2_rn(p, s2, make_float2(kT2, kT2));
+            p = __ffma2_rn(p, s2, make_float2(kT1, kT1));
+            p = __ffma2_rn(p, s2, make_float2(kT0, kT0));
+            t = __fmul2_rn(c, p);
+          } else {
+            t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+          }
 #endif
           const float2 x = __ffma2_rn(a, t, a);  // w * log2(e), in [-0.41, 116]
           float2 e;
