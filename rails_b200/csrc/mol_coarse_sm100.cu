@@ -59,6 +59,10 @@ constexpr float kGateClamp = 40.f;  // clamp of the half gate pre-activation u (
 #define MOL_EX2_EMU_OF4 0  // measured on B200: 0 is fastest ("what did not work")
 #endif
 constexpr int kEx2EmuOf4 = MOL_EX2_EMU_OF4;
+#ifndef MOL_G1_SPLIT
+#define MOL_G1_SPLIT 0  // measured: 35.5 ms split vs 34.4 ms unsplit per 512 x 1M step
+#endif
+constexpr bool kG1Split = MOL_G1_SPLIT != 0;
 #ifndef MOL_E2_POLY_MASK
 #define MOL_E2_POLY_MASK 0x0E
 #endif
@@ -309,11 +313,16 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       uint32_t c1 = 0, c2 = 0;  // completed e1_done / e2_done phases of this slot
       bool first = true, pre_g1 = false;
 
-      auto issue_g1 = [&](int s) __attribute__((always_inline)) {
+      // part 2: the whole G1 + commit; part 0: the first half of the item-group MMAs; part 1: the second half + commit.
+      // Split in two, the next query's (not yet urgent) G1 never holds the in-order tensor pipe for more than half its
+      // length in front of the other slot's G2 / G3, whose epilogue warps are waiting (MOL_G1_SPLIT).
+      auto issue_g1 = [&](int s, int part) __attribute__((always_inline)) {
         const uint32_t sXa = smem_u32(sX + s * C::X_BYTES);
+        const int gb = part == 1 ? C::NG / 2 : 0, ge = part == 0 ? C::NG / 2 : C::NG;
         if (elect_one_sync()) {
 #pragma unroll
           for (int g = 0; g < C::NG; ++g) {
+            if (g < gb || g >= ge) continue;
 #pragma unroll
 #ifdef MOL_ABLATE_G1
             for (int ks = 0; ks < C::K1 / 32; ++ks) {  // (timing experiment: half the K steps)
@@ -326,7 +335,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               umma_ss(base + kColLog + g * 16, da, db, idesc1, ks > 0);
             }
           }
-          umma_commit(&bars->log_full[wg]);
+          if (part != 0) umma_commit(&bars->log_full[wg]);
         }
         __syncwarp();
       };
@@ -351,7 +360,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               mbar_wait_sleep(&bars->q0_ready[wg], 0);
               tc_fence_after();
             }
-            issue_g1(s);
+            issue_g1(s, 2);
           }
           first = false;
           pre_g1 = false;
@@ -376,15 +385,17 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             // the next G1 overwrites LOG / A2 and reads the next query image: the E3 group must have copied the fp16
             // logits of this query out of A2 and staged that image (a2_read)
             if (j + 1 < n || (n_next > 0 && C::STAGES > 1)) mbar_wait_sleep(&bars->a2_read[wg], (c1 - 1u) & 1u);
+            int g1_stage = -1;  // smem stage whose item tile the next G1 of this slot reads (-1: none to issue here)
             if (j + 1 < n) {
-              issue_g1(s);
+              g1_stage = s;
             } else if (n_next > 0 && C::STAGES > 1) {  // (single stage: the next tile cannot land before this one is released)
               const int sn = (it + 1) % C::STAGES;
               mbar_wait_sleep(&bars->full[sn], (uint32_t)((it + 1) / C::STAGES) & 1u);
               tc_fence_after();
-              issue_g1(sn);
+              g1_stage = sn;
               pre_g1 = true;
             }
+            if (g1_stage >= 0) issue_g1(g1_stage, kG1Split ? 0 : 2);
             if (wg == 0) TR(2, 2, c2);
             // ---- G3, first part: needs the first half of A3 (E2), the diag of this query staged and GATE released
             //      by E3 of the previous query (gate_free; its first phase is arrived by the E1/E3 group's prologue)
@@ -411,6 +422,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               }
             }
             __syncwarp();
+            if (kG1Split && g1_stage >= 0) issue_g1(g1_stage, 1);
             if (wg == 0) TR(2, 4, c2);
             // ---- G3, second part, once E2 has written all of A3
             mbar_wait_sleep(&bars->e2_done[wg], c2 & 1u);

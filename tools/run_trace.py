@@ -25,12 +25,21 @@ base = t[0, 0, 0].item()
 A, Bq, I = t[0] - base, t[1] - base, t[2] - base
 import numpy as np
 a = A.numpy(); b = Bq.numpy(); i = I.numpy()
-print("rows: A[p=0] k-th own query: [.,.,.,E3start,gate_full,E3end]; B0 per query: [hid_wait,hid_full,-,e2done,log_wait,log_full]; I per query: [w_e1,e1,g2g1_iss,e2a+gf,g3a_iss,e2b,g3b_iss]")
-for j in list(range(100, 108)):
-    print(j, "A", a[j, 3:6].tolist(), "B", b[j, [4, 5, 0, 1, 3]].tolist(), "I", i[j, :7].tolist())
+# trace events (mol_coarse_sm100.cu TR(role, ev, idx)), slot 0 of CTA 0, idx = the slot's query counter:
+#   issuer  I: 0 before wait e1_done, 1 after, 2 G2 (+ next G1) issued, 3 e2a_done + gate_free seen, 4 G3a issued,
+#              5 e2_done seen, 6 G3b issued
+#   E1/E2   B: 4 before wait log_full, 5 after, 0 E1 done, 1 hid_full seen, 2 first half of A3 written, 3 E2 done
+#   E3      A: 0 before wait e1_done, 1 after, 2 logits copied (a2_read), 3 before wait gate_full (previous query),
+#              4 after, 5 E3 done
 s = slice(40, 200)
-print("issuer period per query:", np.diff(i[s, 0]).mean())
-print("I: wait e1", (i[s, 1] - i[s, 0]).mean(), "issue G2+G1", (i[s, 2] - i[s, 1]).mean(), "wait e2a/gate_free", (i[s, 3] - i[s, 2]).mean(), "issue G3a", (i[s, 4] - i[s, 3]).mean(), "wait e2b", (i[s, 5] - i[s, 4]).mean(), "issue G3b", (i[s, 6] - i[s, 5]).mean())
-print("B0: wait log_full", (b[s, 5] - b[s, 4]).mean(), "E1 work", (b[s, 0] - b[s, 5]).mean(), "wait hid_full", (b[s, 1] - b[s, 0]).mean(), "E2 work", (b[s, 3] - b[s, 1]).mean())
-sa = slice(20, 100)
-print("A0 (every other query): period", np.diff(a[sa, 3]).mean(), "wait gate_full", (a[sa, 4] - a[sa, 3]).mean(), "E3 work", (a[sa, 5] - a[sa, 4]).mean())
+def m(x):
+    return round(float(x[s].mean()), 1)
+print("per-query period of the slot (clk):", m(np.diff(i[:, 0])[39:199]), " -> per (query, tile) unit of the CTA:", m(np.diff(i[:, 0])[39:199]) / 2)
+print("issuer : wait e1_done", m(i[:, 1] - i[:, 0]), "| issue G2+G1", m(i[:, 2] - i[:, 1]), "| wait e2a/gate_free", m(i[:, 3] - i[:, 2]),
+      "| issue G3a", m(i[:, 4] - i[:, 3]), "| wait e2_done", m(i[:, 5] - i[:, 4]), "| issue G3b", m(i[:, 6] - i[:, 5]))
+print("E1/E2  : wait log_full", m(b[:, 5] - b[:, 4]), "| E1", m(b[:, 0] - b[:, 5]), "| wait hid_full", m(b[:, 1] - b[:, 0]),
+      "| E2 first half", m(b[:, 2] - b[:, 1]), "| E2 second half", m(b[:, 3] - b[:, 2]))
+print("E3     : wait e1_done", m(a[:, 1] - a[:, 0]), "| copy logits", m(a[:, 2] - a[:, 1]), "| wait gate_full", m(a[:, 4] - a[:, 3]),
+      "| E3", m(a[:, 5] - a[:, 4]), "| tail (store, next wait)", m(np.roll(a[:, 0], -1) - a[:, 5]))
+for j in range(100, 104):
+    print(j, "I", (i[j, :7] - i[j, 0]).tolist(), "B", (b[j, [4, 5, 0, 1, 2, 3]] - i[j, 0]).tolist(), "A", (a[j, :6] - i[j, 0]).tolist())
