@@ -63,6 +63,10 @@ constexpr int kEx2EmuOf4 = MOL_EX2_EMU_OF4;
 #define MOL_G1_SPLIT 0  // measured: 35.5 ms split vs 34.4 ms unsplit per 512 x 1M step
 #endif
 constexpr bool kG1Split = MOL_G1_SPLIT != 0;
+#ifndef MOL_E1_EARLY
+#define MOL_E1_EARLY 0  // measured: 35.6 ms early vs 34.6 ms at the loop top per 512 x 1M step
+#endif
+constexpr bool kE1Early = MOL_E1_EARLY != 0;
 #ifndef MOL_E2_POLY_MASK
 #define MOL_E2_POLY_MASK 0x0E
 #endif
@@ -461,12 +465,14 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     SlotSeq seq(f0, f1, P.bc, wg);
     int tile = 0, q = 0;
     uint32_t cnt = 0;
-    while (seq.next(tile, q)) {
-      // ---------------- E1
-      if (warp == 4) TR(1, 4, cnt);
-      mbar_wait_sleep(&bars->log_full[wg], cnt & 1u);
+    // E1 of the slot's k-th query.  It runs BETWEEN the two halves of E2 of the previous query (MOL_E1_EARLY): its
+    // log_full has long fired by then, and with e1_done already set the issuer queues G2 of the next query directly
+    // behind G3 of this one, instead of after a round trip through this warpgroup.
+    auto do_e1 = [&](uint32_t k) __attribute__((always_inline)) {
+      if (warp == 4) TR(1, 4, k);
+      mbar_wait_sleep(&bars->log_full[wg], k & 1u);
       tc_fence_after();
-      if (warp == 4) TR(1, 5, cnt);
+      if (warp == 4) TR(1, 5, k);
       {
         uint32_t la[16], lb[16];
         auto conv = [&](const uint32_t* v, uint32_t col) __attribute__((always_inline)) {
@@ -496,8 +502,18 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bars->e1_done[wg]);
+      if (warp == 4) TR(1, 0, k);
+    };
+    bool have = seq.next(tile, q);
+    bool e1_pending = have;  // E1 of query `cnt` still to do at the top of the loop
+    while (have) {
+      const int tile_cur = tile;
+      const bool have_next = seq.next(tile, q);
+      // the next query's G1 is issued before this query's G3 only inside a tile, or across tiles when the next item
+      // tile has its own shared-memory stage; otherwise it waits for e2_done of this query and E1 must not block it
+      const bool e1_early = kE1Early && have_next && (C::STAGES > 1 || tile == tile_cur);
+      if (e1_pending) do_e1(cnt);
       // ---------------- E2
-      if (warp == 4) TR(1, 0, cnt);
       mbar_wait_sleep(&bars->hid_full[wg], cnt & 1u);
       tc_fence_after();
       if (warp == 4) TR(1, 1, cnt);
@@ -552,6 +568,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tc_fence_before();
           mbar_arrive(&bars->e2a_done[wg]);
           if (warp == 4) TR(1, 2, cnt);
+          if (e1_early) do_e1(cnt + 1);  // (va, prefetched for chunk 4, stays live across it)
         }
       }
       tmem_st_x8(base + kColHid + 64, ones);
@@ -560,6 +577,8 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_arrive(&bars->e2_done[wg]);
       if (warp == 4) TR(1, 3, cnt);
       ++cnt;
+      have = have_next;
+      e1_pending = have_next && !e1_early;
     }
   } else if (warp < kCtlWarp0) {
     // =============================== E3 warpgroup of slot `wg` (+ query staging) ===============================
