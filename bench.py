@@ -337,7 +337,7 @@ def main():
         "kernel_share_of_step": kern_ms_step / ms_step,
         "hbm_gbs_algorithmic": (n_local * bytes_per_item(cfg)) / (kern_ms_step * 1e-3) / 1e9 if kern_ms_step > 0 else 0.0,
         "hbm_peak_gbs": hbm_peak,
-        "co_limit": "MUFU (H + 2L = 256 transcendentals per pair at the measured 16/clk/SM): 28.7 ms per 512 x 1M step at 1.965 GHz; ncu: XU pipe 79 % active",
+        "co_limit": "MUFU: 208 transcendentals per pair (H + 2L = 256, minus the 48 hidden-unit tanh the kernel evaluates by polynomial on the FMA pipe) at the measured 16/clk/SM: 23.3 ms per 512 x 1M step at 1.965 GHz; tensor-pipe floor with every MUFU op removed: 22.9 ms",
     }
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload
