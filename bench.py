@@ -43,7 +43,7 @@ def parse():
     p.add_argument("--batch", type=int, default=512)
     p.add_argument("--k", type=int, default=100)
     p.add_argument("--mode", default="auto", choices=["auto", "exact", "tensor"])
-    p.add_argument("--cpu-queries", type=int, default=8, help="queries in the cpu_baseline sample")
+    p.add_argument("--cpu-queries", type=int, default=32, help="queries in the cpu_baseline sample (~11 s of CPU work)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
 
@@ -159,10 +159,11 @@ def run_reference(args):
 
     mol, _ = build_module(cfg, None, "cpu", seed=0)
     sd = {k: v.detach() for k, v in mol.state_dict().items()}
-    nq = 2
+    # exactly --steps K timed steps after --warmup W; the sample per step (queries against the full corpus) shrinks with
+    # K + W so that the run stays within a few minutes (~0.34 s of CPU per query on 16 cores)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    nq = max(1, min(8, 240 // (steps + warm)))
     items, ids, q, _ = synthetic_inputs(cfg, args.items, nq, 0, "cpu")
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
     for _ in range(warm):
         cpu_oracle_time(cfg, sd, items, ids, q, args.k)
     t0 = time.perf_counter()

@@ -49,7 +49,10 @@ constexpr int kCtlWarp0 = kEpiThreads / 32;    // control warpgroup: issuer slot
 constexpr int kThreads = kEpiThreads + 4 * 32;
 // setmaxnreg split of the 64K-register file (the kernel is compiled for 640 threads -> 96 registers at launch)
 // (setmaxnreg only redistributes the CTA's own launch allocation: 640 x 96 = 61440 registers)
-constexpr int kE13Regs = 160, kE2Regs = 56, kCtlRegs = 48;
+#ifndef MOL_E2_REGS
+#define MOL_E2_REGS 56
+#endif
+constexpr int kE2Regs = MOL_E2_REGS, kE13Regs = 216 - kE2Regs, kCtlRegs = 48;
 static_assert(256 * kE13Regs + 256 * kE2Regs + 128 * kCtlRegs <= kThreads * 96, "register pool over-committed");
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kK3 = kH + 16;    // K of the gate GEMM's TS part: hidden units + the ones block
