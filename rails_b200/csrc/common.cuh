@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/mol_b200.h"
 
@@ -48,6 +49,18 @@ void count_launch(int n = 1);
   } while (0)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Byte budget of the (rows, N) fp32 score matrices the prefilter / MIPS / per-group paths materialise per launch (default
+// 2 GiB).  MOL_B200_SCORE_MATRIX_BYTES shrinks it so that tests reach the multi-chunk code paths at small N; the
+// *_workspace_bytes and the search call read the same value.
+inline size_t score_matrix_budget() {
+  const char* e = getenv("MOL_B200_SCORE_MATRIX_BYTES");
+  if (e) {
+    const long long v = atoll(e);
+    if (v >= 4096) return (size_t)v;
+  }
+  return (size_t)2 << 30;
+}
 
 // Bump allocator over the caller's workspace.
 struct Arena {

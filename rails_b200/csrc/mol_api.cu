@@ -638,7 +638,7 @@ static int plan_avg(const mol_shape_t& s, int64_t N, int B, int k, int avg_top_k
   ws->w2t = a.take<float>((size_t)D.L * D.H);
   ws->qsum = a.take<float>((size_t)B * D.d);
   const int64_t n = N > 0 ? N : 1;
-  int64_t rows = (int64_t)(2ull << 30) / (int64_t)(sizeof(float) * (size_t)n);
+  int64_t rows = (int64_t)score_matrix_budget() / (int64_t)(sizeof(float) * (size_t)n);
   if (rows < 1) rows = 1;
   if (rows > B) rows = B > 0 ? B : 1;
   ws->rows = (int)rows;
@@ -812,7 +812,7 @@ static int plan_groups(const mol_shape_t& s, int64_t N, int B, int kpg, int avg_
   ws->w2t = a.take<float>((size_t)D.L * D.H);
   ws->qavg = a.take<float>((size_t)B * D.d);
   const int64_t n = N > 0 ? N : 1;
-  int64_t rows = (int64_t)(2ull << 30) / (int64_t)(sizeof(float) * (size_t)n);
+  int64_t rows = (int64_t)score_matrix_budget() / (int64_t)(sizeof(float) * (size_t)n);
   rows = rows / D.Pq * D.Pq;
   if (rows < D.Pq) rows = D.Pq;
   if (rows > (int64_t)B * D.Pq) rows = (int64_t)B * D.Pq;

@@ -132,7 +132,7 @@ int mol_select_valid(const float* scores, const int64_t* ids, const int64_t* inv
 int mol_mips_workspace_bytes(int64_t num_items, int32_t B, int32_t k, size_t* bytes) {
   MOL_CHECK_ARG(bytes && num_items >= 0 && B >= 0 && k >= 1, "bad arguments");
   const int64_t n = num_items > 0 ? num_items : 1;
-  int64_t rows = (int64_t)(2ull << 30) / (int64_t)(sizeof(float) * (size_t)n);
+  int64_t rows = (int64_t)score_matrix_budget() / (int64_t)(sizeof(float) * (size_t)n);
   if (rows < 1) rows = 1;
   if (rows > B) rows = B > 0 ? B : 1;
   size_t topk;
@@ -169,7 +169,7 @@ int mol_mips_search(const float* items, const int64_t* item_ids, const float* qu
     set_error("mips workspace too small: need %zu, got %zu", need, workspace_bytes);
     return MOL_ERR_WORKSPACE;
   }
-  int64_t rows = (int64_t)(2ull << 30) / (int64_t)(sizeof(float) * (size_t)num_items);
+  int64_t rows = (int64_t)score_matrix_budget() / (int64_t)(sizeof(float) * (size_t)num_items);
   if (rows < 1) rows = 1;
   if (rows > B) rows = B;
   float* mat = static_cast<float*>(workspace);

@@ -118,6 +118,49 @@ def test_k_out_of_range_raises_runtime_error_like_torch_topk():
         top(g["queries"].to(DEV), k=g["items"].size(0) + 1)
 
 
+def test_c_abi_error_paths_return_status_not_crash():
+    """The C entry points report bad calls through their int status + mol_last_error(): a workspace
+    that is too small, NULL buffers, a candidate count beyond MOL_MAX_K - and the library keeps working afterwards."""
+    from ctypes import byref
+
+    cfg = CFG_8x8x32
+    mol, _ = build_module(cfg, None, DEV, seed=1)
+    items, ids, q, _ = synthetic_inputs(cfg, 5000, 4, 1, DEV)
+    top = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0))
+    index = top._ensure_index()
+    w = mol.packed_weights(torch.device(DEV))
+    lib = _lib.load()
+    B, k = 4, 10
+    out_s = torch.empty((B, k), dtype=torch.float32, device=DEV)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=DEV)
+    small = torch.empty(1024, dtype=torch.uint8, device=DEV)
+    stream = engine._stream_ptr(torch.device(DEV))
+
+    def call(qp, sp, ip, wsp, nbytes):
+        return lib.mol_search(byref(w.shape), byref(w.struct), byref(index.struct), qp, None, B, k, 1, _lib.MODE_AUTO,
+                              sp, ip, wsp, nbytes, stream)
+
+    P = engine._ptr
+    assert call(P(q), P(out_s), P(out_i), P(small), small.numel()) == 3  # MOL_ERR_WORKSPACE
+    assert b"workspace" in lib.mol_last_error()
+    with pytest.raises(RuntimeError, match="workspace"):
+        _lib.check(3)
+    assert call(None, P(out_s), P(out_i), P(small), small.numel()) == 1  # MOL_ERR_INVALID (NULL queries)
+    with pytest.raises(ValueError):
+        _lib.check(1)
+    # P_Q * P_X * k_per_group beyond MOL_MAX_K: refused up front
+    from rails_b200.indexing.mol_top_k import MoLNaiveTopK
+
+    with pytest.raises(ValueError, match="MOL_MAX_K"):
+        MoLNaiveTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), k_per_group=200)(q, k=10)
+    # k_per_group larger than the corpus: torch.topk's RuntimeError
+    with pytest.raises(RuntimeError, match="out of range"):
+        MoLNaiveTopK(mol, items[:50].unsqueeze(0), ids[:50].unsqueeze(0), k_per_group=64)(q, k=10)
+    # and a normal call still works
+    s, i = top(q, k=k)
+    assert s.shape == (B, k) and bool(torch.isfinite(s).all())
+
+
 def test_empty_batch():
     g = load_golden("edge_tiny")
     mol, _ = build_module(g["cfg"], g["sd"], DEV)
@@ -460,6 +503,35 @@ def test_mol_naive_comb_top_k_large_vs_oracle():
             assert (s[b, :50].cpu() - rs[b, :50]).abs().max().item() < SCORE_TOL
     with pytest.raises(NotImplementedError):
         MoLNaiveTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), kpg, use_faiss=True)
+
+
+def test_chunked_score_matrix_paths_equal_single_chunk(monkeypatch):
+    """MIPS / Avg / Naive / Comb materialise a (rows, N) fp32 matrix per launch and loop over query chunks when it would
+    exceed its byte budget.  With the budget shrunk (MOL_B200_SCORE_MATRIX_BYTES) the same calls take several chunks and
+    must return exactly what the single-chunk run returned."""
+    from rails_b200.indexing.mips_top_k import MIPSBruteForceTopK
+    from rails_b200.indexing.mol_top_k import MoLAvgTopK, MoLCombTopK, MoLNaiveTopK
+
+    cfg = CFG_8x8x32
+    N, B = 6000, 11
+    mol, _ = build_module(cfg, None, DEV, seed=8)
+    items, ids, q, _ = synthetic_inputs(cfg, N, B, 8, DEV)
+    it, idd = items.unsqueeze(0), ids.unsqueeze(0)
+
+    def run_all():
+        return [
+            MIPSBruteForceTopK(it, idd)(q, k=50),
+            MoLAvgTopK(mol, it, idd, 300)(q, k=20),
+            MoLNaiveTopK(mol, it, idd, 4)(q, k=20),
+            MoLCombTopK(mol, it, idd, 120, 3)(q, k=20),
+        ]
+
+    ref = run_all()
+    # 6000 items * 4 B = 24 kB per row: 3 query rows (MIPS / Avg) and one query = 8 group rows (Naive / Comb) per launch
+    monkeypatch.setenv("MOL_B200_SCORE_MATRIX_BYTES", str(N * 4 * 8 + 64))
+    got = run_all()
+    for (rs, ri), (s, i) in zip(ref, got):
+        assert torch.equal(ri, i) and torch.equal(rs, s)
 
 
 # ------------------------------------------------------------------------------- multi-GPU (needs >= 2 devices)
