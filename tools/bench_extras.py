@@ -44,6 +44,12 @@ out["mips_top100_B512_1M_ms"] = timed(lambda: mips(q, k=k))
 inv = torch.randint(1, N + 1, (B, 211), device=dev)
 index = CandidateIndex(ids=ids.unsqueeze(0), embeddings=items.unsqueeze(0))
 out["candidate_index_mol_k100_n0_211_B512_1M_ms"] = timed(lambda: index.get_top_k_outputs(q, k, {}, top, inv))
+# approximate modules of the reference, same corpus; B = 64 (their score matrices are chunked)
+from rails_b200.indexing.mol_top_k import MoLAvgTopK, MoLCombTopK, MoLNaiveTopK
+for name, mod in (("mol_avg_top2000", MoLAvgTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), 2000)),
+                  ("mol_naive_kpg5", MoLNaiveTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), 5)),
+                  ("mol_comb_kpg5_avg200", MoLCombTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), 200, 5))):
+    out[f"{name}_B64_1M_ms"] = timed(lambda: mod(q[:64], k=k), 1, 3)
 # the reference's own configs (BASELINE.json configs[0..2])
 for name, c, n, b, kk in (("cfg1_8x4x64_N3883_B1_k10", CFG_8x4x64, 3883, 1, 10), ("cfg2_8x4x128_N27278_B128_k100", CFG_8x4x128, 27278, 128, 100),
                           ("cfg3_8x8x32_N695762_B256_k200", CFG_8x8x32, 695762, 256, 200)):
