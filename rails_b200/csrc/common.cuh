@@ -142,5 +142,7 @@ int launch_select_final_i64(const float* scores, const int64_t* payload, int64_t
                             int B, int kk, float* out_scores, int64_t* out_ids, cudaStream_t st);
 
 int select_num_segments(int64_t n, int B, int kk);
+int select_num_segments_streamed(int64_t n, int B, int kk);
+int64_t select_streamed_slots(int64_t n, int64_t rows, int kk);
 
 }  // namespace mol

@@ -643,7 +643,7 @@ static int plan_avg(const mol_shape_t& s, int64_t N, int B, int k, int avg_top_k
   if (rows > B) rows = B > 0 ? B : 1;
   ws->rows = (int)rows;
   ws->scores = a.take<float>((size_t)rows * (size_t)n);
-  const size_t seg = (size_t)(rows + 2 * 148 + 1) * (size_t)avg_top_k;
+  const size_t seg = (size_t)select_streamed_slots(n, rows, avg_top_k) * (size_t)avg_top_k;
   ws->seg_scores = a.take<float>(seg);
   ws->seg_idx = a.take<int32_t>(seg);
   ws->cand_scores = a.take<float>((size_t)B * avg_top_k);
@@ -717,7 +717,7 @@ int mol_search_avg(const mol_shape_t* shape, const mol_weights_t* w, const mol_i
     const int nb = (B - b0 < ws.rows) ? (B - b0) : ws.rows;
     // avg_sim_values = q_sum . avg_items^T ; top avg_top_k positions per query (:352-360)
     MOL_TRY(launch_linear(ws.qsum + (size_t)b0 * D.d, avg_items, nullptr, ws.scores, nb, (int)N, D.d, D.d, 1, ACT_NONE, st));
-    const int S = select_num_segments(N, nb, avg_top_k);
+    const int S = select_num_segments_streamed(N, nb, avg_top_k);
     const float* sel = ws.scores;
     const int32_t* pay = nullptr;
     int64_t sn = N, sld = N;
@@ -819,7 +819,7 @@ static int plan_groups(const mol_shape_t& s, int64_t N, int B, int kpg, int avg_
   ws->rows = (int)rows;
   ws->scores = a.take<float>((size_t)rows * (size_t)n);
   const int kmax = kpg > avg_top_k ? kpg : avg_top_k;
-  const size_t seg = (size_t)(rows + 2 * 148 + 1) * (size_t)kmax;
+  const size_t seg = (size_t)select_streamed_slots(n, rows, kmax) * (size_t)kmax;
   ws->seg_scores = a.take<float>(seg);
   ws->seg_idx = a.take<int32_t>(seg);
   ws->sel_scores = a.take<float>((size_t)rows * kmax);
@@ -838,7 +838,7 @@ static int plan_groups(const mol_shape_t& s, int64_t N, int B, int kpg, int avg_
 
 // top-kk column positions (int32) of every row of a (nb, N) matrix
 static int select_positions(const GroupsWs& ws, int64_t N, int nb, int kk, int32_t* out_idx, cudaStream_t st) {
-  const int S = select_num_segments(N, nb, kk);
+  const int S = select_num_segments_streamed(N, nb, kk);
   const float* sel = ws.scores;
   const int32_t* pay = nullptr;
   int64_t sn = N;
@@ -951,8 +951,9 @@ int mol_query_prologue(const mol_shape_t* shape, const mol_weights_t* w, const f
 
 int mol_topk_workspace_bytes(int64_t n, int32_t B, int32_t k, size_t* bytes) {
   MOL_CHECK_ARG(bytes && n >= 0 && B >= 0 && k >= 1, "bad arguments");
-  int S = select_num_segments(n, B > 0 ? B : 1, k);
-  *bytes = 2 * align_up((size_t)(B > 0 ? B : 1) * S * k * sizeof(float), 256) + 512;
+  // slots >= B' * S(B') for every B' <= B: a caller that sizes for its largest chunk can run the smaller ones
+  const size_t slots = (size_t)select_streamed_slots(n, B > 0 ? B : 1, k);
+  *bytes = 2 * align_up(slots * k * sizeof(float), 256) + 512;
   return MOL_OK;
 }
 
@@ -968,7 +969,7 @@ int mol_topk(const float* scores, int64_t n, int64_t ld, int32_t B, int32_t k, c
   if (B == 0) return MOL_OK;
   MOL_CHECK_ARG(scores && out_scores && out_idx, "NULL buffer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int S = select_num_segments(n, B, k);
+  int S = select_num_segments_streamed(n, B, k);
   if (S == 1)
     return launch_select_final_i32(scores, nullptr, n, ld, B, k, out_scores, nullptr, out_idx, id_map, nullptr, st);
   size_t need;

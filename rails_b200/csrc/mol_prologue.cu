@@ -79,8 +79,9 @@ __global__ void __launch_bounds__(256, 2) linear_kernel(const float* __restrict_
     stash();
     __syncthreads();
     if (k0 + LT_K < K) fetch(k0 + LT_K);
+    const int kmax = K - k0 < LT_K ? K - k0 : LT_K;  // (the slab's zero padding is not multiplied: K = d = 32 for the prefilters)
 #pragma unroll 8
-    for (int kk = 0; kk < LT_K; ++kk) {
+    for (int kk = 0; kk < kmax; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
       const float4 b4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
       const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};

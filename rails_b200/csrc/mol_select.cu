@@ -233,6 +233,27 @@ int select_num_segments(int64_t n, int B, int kk) {
   return (int)S;
 }
 
+// Segment count for selects over a MATERIALISED (rows, n) matrix that does not fit the L2 (MIPS, the Avg / Naive / Comb
+// prefilters): segments of <= 32k elements (128 KB), so that the four passes of the radix select over a segment (three
+// histograms + the emit) read HBM once and the L2 afterwards - ~600 resident CTAs x 128 KB stay below the 126 MB L2.
+int select_num_segments_streamed(int64_t n, int B, int kk) {
+  int64_t S = select_num_segments(n, B, kk);
+  int64_t min_seg = 16384;
+  if (min_seg < 4 * (int64_t)kk) min_seg = 4 * (int64_t)kk;
+  int64_t s_max = n / min_seg;
+  if (s_max < 1) s_max = 1;
+  if (s_max > 256) s_max = 256;
+  int64_t want = (n + 32767) / 32768;
+  if (want > s_max) want = s_max;
+  return (int)(want > S ? want : S);
+}
+// Upper bound of rows' * select_num_segments_streamed(n, rows', kk) over rows' <= rows (workspace sizing).
+int64_t select_streamed_slots(int64_t n, int64_t rows, int kk) {
+  const int64_t a = rows + 2 * 148 + 1;
+  const int64_t b = rows * (int64_t)select_num_segments_streamed(n, 1 << 30, kk);
+  return a > b ? a : b;
+}
+
 // Public launchers ------------------------------------------------------------------------------
 int launch_select_segments(const float* scores, int64_t n, int64_t ld, int B, int S, int kk,
                            float* cand_scores, int32_t* cand_idx, const int32_t* query_flags,
