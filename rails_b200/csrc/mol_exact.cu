@@ -456,7 +456,9 @@ static int launch_exact_nw(const ExactParams& P, int B, size_t smem, cudaStream_
   MOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t groups = (P.n_per_query + PT - 1) / PT;
   const int64_t work = (int64_t)B * groups;  // upper bound (query_flags may deactivate queries)
-  int64_t blocks = (work + NW - 1) / NW;
+  // small launches (the rescoring pass of a few queries) spread one work item per block over up to 148 SMs instead of
+  // filling the 8 warps of a few blocks: the passes run in parallel and each block's 64 KB weight copy is cheap
+  int64_t blocks = work;
   if (blocks > 148) blocks = 148;
   if (blocks < 1) blocks = 1;
   kern<<<(unsigned)blocks, NW * 32, smem, st>>>(P);

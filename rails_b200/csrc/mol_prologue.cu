@@ -107,9 +107,138 @@ __global__ void __launch_bounds__(256, 2) linear_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// W-resident variant for the index build (M = corpus size, N * K small): persistent blocks keep the whole weight
+// matrix in shared memory (k-major, read as float4 along n), walk the 64-row tiles of A with the next tile
+// prefetched into registers, and give every thread a 4 x (4 * NJ) register tile (5 LDS.128 per 64 FMAs at NJ = 4).
+// Same per-element arithmetic as linear_kernel: acc = 0, fmaf over k ascending, + bias, optional silu.
+// ------------------------------------------------------------------------------------------
+constexpr int WR_TM = 64;
+
+template <int ACT, int NJ, int K>
+__global__ void __launch_bounds__(256, 2) linear_wres_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                                                             const float* __restrict__ bias, float* __restrict__ C,
+                                                             int64_t M, int64_t w_sn, int64_t w_sk) {
+  constexpr int N = 64 * NJ;
+  extern __shared__ __align__(16) float wr_smem[];
+  float* Ws = wr_smem;                // [K][N + 4]
+  float* As = Ws + (size_t)K * (N + 4);  // [K][WR_TM + 4]
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  for (int e = tid; e < N * K; e += 256) {
+    int n, k;
+    if (w_sk == 1) {
+      n = e / K;
+      k = e % K;
+    } else {
+      k = e / N;
+      n = e % N;
+    }
+    Ws[k * (N + 4) + n] = __ldg(W + n * w_sn + k * w_sk);
+  }
+  constexpr int k4 = K / 4;             // float4 per row of A
+  constexpr int per_thread = WR_TM * k4 / 256;
+  static_assert(WR_TM * k4 % 256 == 0, "A tile must split evenly over the block");
+  float4 ra[per_thread];
+  const int64_t tiles = (M + WR_TM - 1) / WR_TM;
+  auto fetch = [&](int64_t tile) {
+#pragma unroll
+    for (int u = 0; u < per_thread; ++u) {
+      const int e = tid + u * 256;
+      const int r = e / k4, c = e % k4;
+      const int64_t m = tile * WR_TM + r;
+      ra[u] = (m < M) ? __ldg(reinterpret_cast<const float4*>(A + m * K) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int u = 0; u < per_thread; ++u) {
+      const int e = tid + u * 256;
+      const int r = e / k4, c = e % k4;
+      As[(4 * c + 0) * (WR_TM + 4) + r] = ra[u].x;
+      As[(4 * c + 1) * (WR_TM + 4) + r] = ra[u].y;
+      As[(4 * c + 2) * (WR_TM + 4) + r] = ra[u].z;
+      As[(4 * c + 3) * (WR_TM + 4) + r] = ra[u].w;
+    }
+  };
+  int64_t tile = blockIdx.x;
+  if (tile < tiles) fetch(tile);
+  for (; tile < tiles; tile += gridDim.x) {
+    __syncthreads();  // the previous tile's As reads are done (and, first time, Ws is complete)
+    stash();
+    __syncthreads();
+    if (tile + gridDim.x < tiles) fetch(tile + gridDim.x);
+    float acc[4][4 * NJ];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4 * NJ; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(As + k * (WR_TM + 4) + ty * 4);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float4 b4 = *reinterpret_cast<const float4*>(Ws + k * (N + 4) + 64 * j + tx * 4);
+        const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[i][4 * j + jj] = fmaf(a[i], b[jj], acc[i][4 * j + jj]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = tile * WR_TM + ty * 4 + i;
+      if (m >= M) continue;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int n = 64 * j + tx * 4;
+        float v[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          v[jj] = acc[i][4 * j + jj] + (bias ? bias[n + jj] : 0.f);
+          if (ACT == ACT_SILU) v[jj] = v[jj] / (1.f + expf(-v[jj]));
+        }
+        *reinterpret_cast<float4*>(C + m * N + n) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+}
+
+template <int ACT>
+static bool try_launch_wres(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K,
+                            int64_t w_sn, int64_t w_sk, cudaStream_t st) {
+  // (N = 64 leaves a 4 x 4 register tile per thread: measured slower than the plain tiled kernel, 686 vs 635 us per 1M rows)
+  if (M < 16384 || (K != 64 && K != 128) || (N != 128 && N != 256)) return false;
+  if (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(C)) & 15) != 0) return false;
+  const size_t smem = ((size_t)K * (N + 4) + (size_t)K * (WR_TM + 4)) * sizeof(float);
+  if (smem > 100 * 1024) return false;
+  const int64_t tiles = (M + WR_TM - 1) / WR_TM;
+  const unsigned grid = (unsigned)(tiles < 296 ? tiles : 296);
+#define MOL_WRES_K(NJ, KK)                                                                                          \
+  {                                                                                                                   \
+    cudaFuncSetAttribute(linear_wres_kernel<ACT, NJ, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    linear_wres_kernel<ACT, NJ, KK><<<grid, 256, smem, st>>>(A, W, bias, C, M, w_sn, w_sk);                            \
+  }
+#define MOL_WRES(NJ)                          \
+  {                                           \
+    if (K == 64) MOL_WRES_K(NJ, 64) else MOL_WRES_K(NJ, 128) \
+  }
+  if (N == 128) MOL_WRES(2) else MOL_WRES(4)
+#undef MOL_WRES
+#undef MOL_WRES_K
+  return true;
+}
+
 int launch_linear(const float* A, const float* W, const float* bias, float* C, int64_t M, int N,
                   int K, int64_t w_sn, int64_t w_sk, Act act, cudaStream_t st) {
   if (M == 0 || N == 0) return MOL_OK;
+  if (act == ACT_SILU ? try_launch_wres<ACT_SILU>(A, W, bias, C, M, N, K, w_sn, w_sk, st)
+                      : try_launch_wres<ACT_NONE>(A, W, bias, C, M, N, K, w_sn, w_sk, st)) {
+    MOL_LAUNCH_CHECK();
+    return MOL_OK;
+  }
   dim3 grid((unsigned)((M + LT_M - 1) / LT_M), (unsigned)((N + LT_N - 1) / LT_N));
   if (act == ACT_SILU)
     linear_kernel<ACT_SILU><<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K, w_sn, w_sk);
