@@ -70,6 +70,13 @@ constexpr bool kG1Split = MOL_G1_SPLIT != 0;
 #define MOL_E1_EARLY 0  // measured: 35.6 ms early vs 34.6 ms at the loop top per 512 x 1M step
 #endif
 constexpr bool kE1Early = MOL_E1_EARLY != 0;
+#ifndef MOL_G1_PAIR
+#define MOL_G1_PAIR 0
+#endif
+// slot 0's issuer issues the G1 MMAs of BOTH slots back to back per item-tile slice (collector::a::fill -> ::lastuse, the
+// second MMA skips the 4 KB shared-memory fetch of A: 26.6 instead of 39.9 clk per MMA)
+constexpr bool kG1Pair = MOL_G1_PAIR != 0;
+static_assert(!(kG1Pair && kG1Split), "MOL_G1_PAIR and MOL_G1_SPLIT are exclusive");
 #ifndef MOL_E2_POLY_MASK
 #define MOL_E2_POLY_MASK 0x0E
 #endif
@@ -177,7 +184,9 @@ struct Bars {
   uint64_t full[2], empty[2];
   uint64_t q0_ready[2], e1_done[2], a2_read[2], e2a_done[2], e2_done[2], gate_free[2];
   uint64_t log_full[2], hid_full[2], gate_full[2];
+  uint64_t g1_req;       // MOL_G1_PAIR: slot 1 is ready for its next G1 (arrived by its issuer, consumed by slot 0's)
   uint32_t tmem_base;
+  uint32_t issue_lock;   // MOL_G1_PAIR: held while a fill -> lastuse group is open / while slot 1's issuer issues
 };
 
 // Walks this CTA's flat range of (tile, query) units tile by tile.
@@ -267,6 +276,8 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_init(&bars->hid_full[s], 1);
       mbar_init(&bars->gate_full[s], 1);
     }
+    mbar_init(&bars->g1_req, 1);
+    bars->issue_lock = 0u;
     fence_mbar_init();
   }
   if (warp == kCtlWarp0) tmem_alloc<512>(&bars->tmem_base);
@@ -347,6 +358,58 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         __syncwarp();
       };
 
+      // ---- MOL_G1_PAIR ------------------------------------------------------------------------------------------
+      // Both slots walk the same tiles; inside a tile slot 0 holds the queries qa, qa+2, ... and slot 1 qa+1, qa+3, ...,
+      // so the p-th query of slot 0 and the p-th of slot 1 read the same item tile: their G1s are issued as one
+      // sequence by slot 0's issuer.  Slot 1's issuer announces "LOG free + image staged" on g1_req at the points where
+      // it would have issued its own G1, and takes issue_lock around its other MMA groups, because an MMA landing
+      // between a collector fill and its lastuse would replace the buffered A slice.
+      uint32_t pc = 0;  // paired G1s issued so far (slot 0) -> phase of g1_req
+      auto lock_issue = [&]() __attribute__((always_inline)) {  // (elected lane only)
+        while (atomicCAS(&bars->issue_lock, 0u, 1u) != 0u) __nanosleep(32);
+      };
+      auto unlock_issue = [&]() __attribute__((always_inline)) { atomicExch(&bars->issue_lock, 0u); };
+      auto issue_g1_pair = [&](int s) __attribute__((always_inline)) {
+        const uint32_t sXa = smem_u32(sX + s * C::X_BYTES);
+        const uint32_t sQ0 = smem_u32(sQ), sQ1 = smem_u32(sQ + C::Q_BYTES);
+        if (elect_one_sync()) {
+          lock_issue();
+#pragma unroll
+          for (int g = 0; g < C::NG; ++g) {
+#pragma unroll
+            for (int ks = 0; ks < C::K1 / 16; ++ks) {
+              const int e = g * C::K1 + ks * 16;
+              const uint64_t da = make_smem_desc(sXa + (e / 64) * 16384 + (e % 64) * 2, 16, 1024, 2);
+              const uint64_t db0 = make_smem_desc(sQ0 + ks * 256, 128, (C::K1 / 8) * 128, 0);
+              const uint64_t db1 = make_smem_desc(sQ1 + ks * 256, 128, (C::K1 / 8) * 128, 0);
+              umma_ss_coll<1>(tmem + kColLog + g * 16, da, db0, idesc1, ks > 0);
+              umma_ss_coll<3>(tmem + 256u + kColLog + g * 16, da, db1, idesc1, ks > 0);
+            }
+          }
+          umma_commit(&bars->log_full[0]);
+          umma_commit(&bars->log_full[1]);
+          unlock_issue();
+        }
+        __syncwarp();
+      };
+      // the G1 of this slot's query number `p` (within its tile, whose slot-1 query count is n1) from stage `s`
+      auto do_g1 = [&](int s, int p, int n1, int part) __attribute__((always_inline)) {
+        if (!kG1Pair) {
+          issue_g1(s, part);
+        } else if (wg == 1) {
+          if (lane == 0) mbar_arrive(&bars->g1_req);
+          __syncwarp();
+        } else if (p < n1) {
+          mbar_wait_sleep(&bars->g1_req, pc & 1u);
+          ++pc;
+          tc_fence_after();
+          issue_g1_pair(s);
+        } else {
+          issue_g1(s, 2);  // odd query count in this tile: slot 0's last query has no partner
+        }
+      };
+      const bool locked = kG1Pair && wg == 1;  // slot 1's issuer serialises its MMA groups against open pairs
+
       TileWalk w(f0, f1, P.bc);
       int it = 0;
       bool have = w.next();
@@ -367,7 +430,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               mbar_wait_sleep(&bars->q0_ready[wg], 0);
               tc_fence_after();
             }
-            issue_g1(s, 2);
+            do_g1(s, 0, w.n_mine(1), 2);
           }
           first = false;
           pre_g1 = false;
@@ -381,12 +444,14 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             ++c1;
             tc_fence_after();
             if (elect_one_sync()) {
+              if (locked) lock_issue();
 #pragma unroll
               for (int ks = 0; ks < C::K2 / 16; ++ks) {
                 const uint64_t db = make_smem_desc(sW1a + ks * 256, 128, (C::K2 / 8) * 128, 0);
                 umma_ts(base + kColHid, base + kColLog + ks * 8, db, idesc2, ks > 0);
               }
               umma_commit(&bars->hid_full[wg]);
+              if (locked) unlock_issue();
             }
             __syncwarp();
             // the next G1 overwrites LOG / A2 and reads the next query image: the E3 group must have copied the fp16
@@ -402,7 +467,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               g1_stage = sn;
               pre_g1 = true;
             }
-            if (g1_stage >= 0) issue_g1(g1_stage, kG1Split ? 0 : 2);
+            if (g1_stage >= 0) do_g1(g1_stage, g1_stage == s && j + 1 < n ? j + 1 : 0, j + 1 < n ? w.n_mine(1) : wn.n_mine(1), kG1Split ? 0 : 2);
             if (wg == 0) TR(2, 2, c2);
             // ---- G3, first part: needs the first half of A3 (E2), the diag of this query staged and GATE released
             //      by E3 of the previous query (gate_free; its first phase is arrived by the E1/E3 group's prologue)
@@ -411,6 +476,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             tc_fence_after();
             if (wg == 0) TR(2, 3, c2);
             if (elect_one_sync()) {
+              if (locked) lock_issue();
 #pragma unroll
 #ifdef MOL_ABLATE_DIAG
               for (int ks = 0; ks < 1; ++ks) {  // (timing experiment: one SS k-step only)
@@ -427,6 +493,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
                 umma_ts(base + kColGate, base + kColHid + ks * 8, db, idesc3, 1u);
               }
+              if (locked) unlock_issue();
             }
             __syncwarp();
             if (kG1Split && g1_stage >= 0) issue_g1(g1_stage, 1);
@@ -437,6 +504,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             ++c2;
             tc_fence_after();
             if (elect_one_sync()) {
+              if (locked) lock_issue();
 #pragma unroll
               for (int ks = 4; ks < kK3 / 16; ++ks) {  // += [A3[:, 64:128] | 1] . [0.5 W2[:, 64:128] | 0.5 b2]^T
                 const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
@@ -444,6 +512,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               }
               umma_commit(&bars->gate_full[wg]);
               if (j == n - 1) umma_commit(&bars->empty[s]);  // every MMA of this slot that reads stage s is issued
+              if (locked) unlock_issue();
             }
             __syncwarp();
             if (wg == 0) TR(2, 6, c2 - 1);
