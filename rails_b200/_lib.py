@@ -155,6 +155,18 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+def build_knobs() -> dict:
+    """Compile-time tuning knobs of the loaded library, parsed from mol_version()'s "[name=value ...]" suffix
+    (ints; e.g. {"e2poly": 14, "e2h2": 0, ...}).  A tuning variant loaded through MOL_B200_LIB reports its own."""
+    v = load().mol_version().decode()
+    out = {}
+    if "[" in v:
+        for tok in v[v.index("[") + 1 : v.rindex("]")].split():
+            name, _, val = tok.partition("=")
+            out[name] = int(val, 0)
+    return out
+
+
 def check(status: int) -> None:
     """Maps the C status to the exception type the reference raises at this boundary."""
     if status == MOL_OK:
@@ -166,6 +178,6 @@ def check(status: int) -> None:
 
 
 __all__ = [
-    "MolShape", "MolWeights", "MolIndex", "load", "check", "byref", "c_size_t", "c_int32", "c_void_p",
+    "MolShape", "MolWeights", "MolIndex", "load", "check", "build_knobs", "byref", "c_size_t", "c_int32", "c_void_p",
     "MODE_AUTO", "MODE_EXACT", "MODE_TENSOR", "MOL_MAX_K", "EXPORTED_SYMBOLS", "LIB_PATH",
 ]

@@ -383,7 +383,14 @@ using namespace mol;
 
 extern "C" {
 
-const char* mol_version(void) { return "rails_b200 0.1 (sm_100a)"; }
+const char* mol_version(void) {
+  static const char* const v = [] {  // thread-safe one-time initialisation
+    static char buf[192];
+    snprintf(buf, sizeof(buf), "rails_b200 0.1 (sm_100a) [%s]", coarse_build_knobs());
+    return buf;
+  }();
+  return v;
+}
 const char* mol_last_error(void) { return g_err; }
 int64_t mol_launch_count(void) { return g_launches.load(); }
 void mol_launch_count_reset(void) { g_launches.store(0); }

@@ -25,6 +25,9 @@ struct CoarseOut {
   int cand_cap;
 };
 
+// compile-time tuning knobs of this build, e.g. "e2poly=0x0E e2h2=0x00 e3h2=0 h2lite=0" (reported through mol_version();
+// tests/test_gpu_parity.py configures the CPU numerics model from it when a tuning variant is loaded)
+const char* coarse_build_knobs();
 void* coarse_trace_buffer();  // debug (MOL_TRACE builds): device buffer for stage timestamps, or nullptr
 bool coarse_supported(const mol_shape_t& s);
 void coarse_plan(const mol_shape_t& s, int chunk, Arena& a, CoarseWs* ws);

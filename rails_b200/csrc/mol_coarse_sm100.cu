@@ -116,6 +116,63 @@ constexpr float kT0 = 0.996860146522522f, kT1 = -0.3149697482585907f, kT2 = 0.10
                 kT6 = 2.547265285102185e-05f, kT7 = -9.067708219845372e-07f, kT8 = 1.3707315282829313e-08f;
 #endif
 
+// ---- MUFU-free silu(2u) in packed half2 (design + constants: tools/fit_silu_h2.py; not yet measured on the GPU) ------
+//   silu(2u) = (u + |u|) - s(|u|),   s(a) = a (1 - tanh a) in [0, 0.28]  ~  a * w * Q(w),   w = relu(1 - a/A)^4
+// u + |u| is exact in fp16 and s is small, so the fp16 evaluation is well conditioned (a polynomial for tanh is not):
+// max |error of h| 2.7e-3, rms 3.5e-4 over every fp16 u in [-12, 12] - the MUFU.TANH.F16 path has 2.9e-3 / 2.7e-4 before the
+// MUFU's own error.  10 half2 instructions per pair of values after the f32 -> f16x2 pack, none of them on the MUFU.
+#ifndef MOL_E2_H2_MASK
+#define MOL_E2_H2_MASK 0
+#endif
+// bit c set: chunk c (16 hidden units) of E2 uses the half2 form (takes precedence over MOL_E2_POLY_MASK for that chunk)
+constexpr unsigned kE2H2Mask = MOL_E2_H2_MASK;
+#ifndef MOL_E3_H2_OF4
+#define MOL_E3_H2_OF4 0
+#endif
+// of every 4 logit pairs of E3, how many take s(|u|) from the half2 form (the large part u + |u| stays in fp32)
+constexpr int kE3H2Of4 = MOL_E3_H2_OF4;
+#ifndef MOL_H2_LITE
+#define MOL_H2_LITE 0
+#endif
+constexpr uint32_t h2x2(unsigned bits16) { return (uint32_t)bits16 * 0x00010001u; }
+constexpr uint32_t kH2One = h2x2(0x3C00);
+#if MOL_H2_LITE
+// A = 5.5, Q of degree 1: 8 instructions, max |error| 7.4e-3, rms 2.7e-3
+constexpr uint32_t kH2NegInvA = h2x2(0xB1D1);
+constexpr uint32_t kH2NC0 = h2x2(0xABCE), kH2NC1 = h2x2(0xBC2C), kH2NC2 = 0u, kH2NC3 = 0u;
+#else
+// A = 6, Q of degree 3 (negated coefficients: -0.05252, -0.35986, -1.68262, +1.09277)
+constexpr uint32_t kH2NegInvA = h2x2(0xB155);
+constexpr uint32_t kH2NC0 = h2x2(0xAAB9), kH2NC1 = h2x2(0xB5C2), kH2NC2 = h2x2(0xBEBB), kH2NC3 = h2x2(0x3C5F);
+#endif
+// a = |u|, aw = a * w, nq = -Q(w)   ->   -s(|u|) = aw * nq
+__device__ __forceinline__ void h2_bump_parts(uint32_t u2, uint32_t& a, uint32_t& aw, uint32_t& nq) {
+  a = u2 & 0x7fff7fffu;
+  uint32_t y = fma_relu_f16x2(a, kH2NegInvA, kH2One);
+  y = mul_f16x2(y, y);
+  const uint32_t w = mul_f16x2(y, y);
+  aw = mul_f16x2(a, w);
+#if MOL_H2_LITE
+  nq = fma_f16x2(kH2NC1, w, kH2NC0);
+#else
+  nq = fma_f16x2(kH2NC3, w, kH2NC2);
+  nq = fma_f16x2(nq, w, kH2NC1);
+  nq = fma_f16x2(nq, w, kH2NC0);
+#endif
+}
+// silu(2u) for two packed fp16 values
+__device__ __forceinline__ uint32_t silu2_h2(uint32_t u2) {
+  uint32_t a, aw, nq;
+  h2_bump_parts(u2, a, aw, nq);
+  return fma_f16x2(aw, nq, add_f16x2(u2, a));
+}
+// -s(|u|) for two packed fp16 values
+__device__ __forceinline__ uint32_t neg_bump_h2(uint32_t u2) {
+  uint32_t a, aw, nq;
+  h2_bump_parts(u2, a, aw, nq);
+  return mul_f16x2(aw, nq);
+}
+
 // TMEM column map of one slot (256 columns)
 constexpr uint32_t kColLog = 0;     // LOG fp32 [0, L); A2 fp16 aliases [0, L/2) + ones [L/2, L/2 + 8)
 constexpr uint32_t kColHid = 64;    // HID fp32 [64, 192); A3 fp16 aliases [64, 128) + ones [128, 136)
@@ -590,11 +647,13 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tc_fence_after();
       if (warp == 4) TR(1, 1, cnt);
       uint32_t va[16], vb[16];
-      auto act = [&](const uint32_t* v, uint32_t col, unsigned poly) __attribute__((always_inline)) {
+      auto act = [&](const uint32_t* v, uint32_t col, unsigned poly, bool h2) __attribute__((always_inline)) {
         uint32_t hk[8];  // bit j2 of `poly`: pair j2 of this chunk takes tanh from the polynomial (FMA pipe), else MUFU.TANH
 #pragma unroll
         for (int j2 = 0; j2 < 8; ++j2) {
-          if ((poly >> j2) & 1u) {
+          if (h2) {  // whole chunk MUFU-free in packed half2 (MOL_E2_H2_MASK)
+            hk[j2] = silu2_h2(pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1])));
+          } else if ((poly >> j2) & 1u) {
             const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
             const float2 c = make_float2(clamp_sym(u.x, kTanhC), clamp_sym(u.y, kTanhC));
             const float2 s2 = __fmul2_rn(c, c);
@@ -631,10 +690,11 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int c = 0; c < 8; c += 2) {
         tmem_ld_wait_bind16(va);
         tmem_ld_x16(base + kColHid + 16 * (c + 1), vb);
-        act(va, kColHid + 8 * c, (unsigned)((kE2Poly64 >> (8 * c)) & 0xffull));
+        act(va, kColHid + 8 * c, (unsigned)((kE2Poly64 >> (8 * c)) & 0xffull), ((kE2H2Mask >> c) & 1u) != 0);
         tmem_ld_wait_bind16(vb);
         if (c + 2 < 8) tmem_ld_x16(base + kColHid + 16 * (c + 2), va);
-        act(vb, kColHid + 8 * (c + 1), (unsigned)((kE2Poly64 >> (8 * (c + 1))) & 0xffull));
+        act(vb, kColHid + 8 * (c + 1), (unsigned)((kE2Poly64 >> (8 * (c + 1))) & 0xffull),
+            ((kE2H2Mask >> (c + 1)) & 1u) != 0);
         if (c == 2) {  // first half of A3 (k < 64) is in TMEM: the issuer may start G3
           tmem_st_wait();
           tc_fence_before();
@@ -758,6 +818,13 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             u.y = fminf(u.y, kGateClamp);
           }
           const float2 a = __fmul2_rn(u, l2e2);
+          float2 x;  // w * log2(e), w = silu(2u), in [-0.41, 116]
+          if ((j2 & 3) >= 4 - kE3H2Of4) {
+            // MUFU-free: w = (u + |u|) - s(|u|); the small bump s in packed half2, the large part in fp32
+            const uint32_t ns2 = neg_bump_h2(pack_f16x2(u.x, u.y));
+            const float2 ns = __half22float2(*reinterpret_cast<const __half2*>(&ns2));
+            x = __ffma2_rn(ns, l2e2, make_float2(a.x + fabsf(a.x), a.y + fabsf(a.y)));
+          } else {
 #ifdef MOL_ABLATE_E3
           const float2 t = u;
 #else
@@ -778,7 +845,8 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
           }
 #endif
-          const float2 x = __ffma2_rn(a, t, a);  // w * log2(e), in [-0.41, 116]
+          x = __ffma2_rn(a, t, a);
+          }
           float2 e;
           if ((j2 & 3) < kEx2EmuOf4) {
             // 2^x on the FMA pipe: x = n + f, n = round(x) through the 1.5*2^23 trick, 2^f by a cubic (7.5e-5 rel.),
@@ -1590,6 +1658,13 @@ static int encode_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t r
 }
 
 static void* g_trace = nullptr;
+#define MOL_STR2(x) #x
+#define MOL_STR(x) MOL_STR2(x)
+const char* coarse_build_knobs() {
+  return "e2poly=" MOL_STR(MOL_E2_POLY_MASK) " e2h2=" MOL_STR(MOL_E2_H2_MASK) " e3poly=" MOL_STR(MOL_E3_POLY_OF4)
+         " e3h2=" MOL_STR(MOL_E3_H2_OF4) " h2lite=" MOL_STR(MOL_H2_LITE) " ex2emu=" MOL_STR(MOL_EX2_EMU_OF4);
+}
+
 void* coarse_trace_buffer() { return g_trace; }
 extern "C" void mol_debug_set_trace(void* p) { g_trace = p; }
 

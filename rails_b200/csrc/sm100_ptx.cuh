@@ -300,6 +300,21 @@ __device__ __forceinline__ uint32_t fma_f16x2(uint32_t a, uint32_t b, uint32_t c
   asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
+__device__ __forceinline__ uint32_t mul_f16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t add_f16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t fma_relu_f16x2(uint32_t a, uint32_t b, uint32_t c) {  // max(a * b + c, 0)
+  uint32_t d;
+  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 // sign(x) * min(|x|, c) for c > 0: a symmetric clamp in one ALU instruction
 __device__ __forceinline__ float clamp_sym(float x, float c) {
   float y;

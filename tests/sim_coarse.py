@@ -18,7 +18,48 @@ def _h(x):
     return x.to(torch.float16).to(torch.float32)
 
 
-def coarse_scores(cfg, sd, queries, items, user_ids=None):
+# fp16 constants of the MUFU-free half2 silu(2u) (tools/fit_silu_h2.py; csrc/mol_coarse_sm100.cu kH2*)
+_H2 = {
+    False: dict(inv_a=-0.16666667, nc=(-0.052520752, -0.35986328, -1.6826172, 1.0927734)),  # A = 6, Q degree 3
+    True: dict(inv_a=-0.18181818, nc=(-0.060974121, -1.0429688)),                            # MOL_H2_LITE
+}
+
+
+def _fma16(a, b, c):
+    return _h(a * b + c)  # fp16 operands: the fp32 product is exact; one fp32 + one fp16 rounding of the sum
+
+
+def _h2_parts(u16, lite=False):
+    """a = |u|, aw = a * relu(1 - a/A)^4, nq = -Q(w): the kernel's h2_bump_parts, one fp16 rounding per instruction."""
+    k = _H2[lite]
+    a = u16.abs()
+    y = torch.relu(_fma16(a, _h(torch.tensor(k["inv_a"])), 1.0))
+    y = _h(y * y)
+    w = _h(y * y)
+    aw = _h(a * w)
+    nc = [_h(torch.tensor(v)) for v in k["nc"]]
+    nq = nc[-1].expand_as(w)
+    for c in reversed(nc[:-1]):
+        nq = _fma16(nq, w, c)
+    return a, aw, nq
+
+
+def silu2_h2(u, lite=False):
+    """silu(2u) by the half2 form: (u + |u|) - s(|u|), everything in fp16 (E2)."""
+    u16 = _h(u)
+    a, aw, nq = _h2_parts(u16, lite)
+    return _fma16(aw, nq, _h(u16 + a))
+
+
+def silu2_h2_f32(u, lite=False):
+    """E3 form: the bump -s(|u|) in half2, the large part u + |u| and the sum in fp32."""
+    a, aw, nq = _h2_parts(_h(u), lite)
+    return (u + u.abs()) + _h(aw * nq)
+
+
+def coarse_scores(cfg, sd, queries, items, user_ids=None, e2_h2_mask=0, e3_h2_of4=0, lite=False):
+    """e2_h2_mask / e3_h2_of4 / lite model the kernel's MOL_E2_H2_MASK / MOL_E3_H2_OF4 / MOL_H2_LITE build knobs
+    (default 0: the shipped kernel; the fp32 polynomial chunks of MOL_E2_POLY_MASK are modelled as exact tanh)."""
     sd = {k: v.float() for k, v in sd.items()}
     q = queries.float()
     qs = O.query_sub_embeddings(cfg, sd, q, user_ids)          # (B, Pq, d) fp32 (exact prologue)
@@ -31,12 +72,24 @@ def coarse_scores(cfg, sd, queries, items, user_ids=None):
     u = _h(torch.nn.functional.linear(_h(logits), w1h) + _h(0.5 * sd[O.K_QI_B1]))
     t = _h(torch.tanh(u))
     h = _h(u + u * t)
+    if e2_h2_mask:
+        unit = torch.arange(u.size(-1))
+        sel = ((e2_h2_mask >> (unit // 16)) & 1).bool()  # chunk c = hidden units [16c, 16c + 16)
+        h = torch.where(sel, silu2_h2(u, lite), h)
     ug = (
         torch.nn.functional.linear(h, w2h)
         + _h(0.5 * gq).unsqueeze(1) * _h(gi).unsqueeze(0)
         + _h(0.5 * sd[O.K_QI_B2])
     )
     w = ug + ug * torch.tanh(ug)
+    if e3_h2_of4:
+        # the kernel walks the logits in its own order l' = m * P_Q + n, two per packed pair; pair j2 of a 16-column
+        # chunk is selected when (j2 & 3) >= 4 - of4
+        l = torch.arange(w.size(-1))
+        PQ, PX = cfg.query_dot_product_groups, cfg.item_dot_product_groups
+        lk = (l % PX) * PQ + (l // PX)
+        sel = ((lk // 2) % 4) >= 4 - e3_h2_of4
+        w = torch.where(sel, silu2_h2_f32(ug, lite), w)
     p = torch.softmax(w, dim=-1)
     return (p * logits).sum(-1)
 

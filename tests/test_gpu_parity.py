@@ -337,7 +337,9 @@ def test_coarse_pass_matches_its_numerics_model(cfg, N, B, seed):
     got = engine.score_all(w, idx, mol.workspace(torch.device(DEV)), q, uid, coarse=True).cpu()
     sd = {k_: v.detach().cpu() for k_, v in mol.state_dict().items()}
     ucpu = None if uid is None else uid.cpu()
-    sim = coarse_scores(cfg, sd, q.cpu(), items.cpu(), ucpu)
+    knobs = _lib.build_knobs()  # a tuning variant (MOL_B200_LIB) is compared with the model of ITS activation forms
+    sim = coarse_scores(cfg, sd, q.cpu(), items.cpu(), ucpu, e2_h2_mask=knobs.get("e2h2", 0),
+                        e3_h2_of4=knobs.get("e3h2", 0), lite=bool(knobs.get("h2lite", 0)))
     exact = O.similarity(cfg, sd, q.cpu(), items.cpu(), ucpu)
     err_sim = (got - sim).abs().max().item()
     err_exact = (got - exact).abs().max().item()
