@@ -173,6 +173,15 @@ __device__ __forceinline__ uint32_t neg_bump_h2(uint32_t u2) {
   return mul_f16x2(aw, nq);
 }
 
+#ifndef MOL_E2_SHARE
+#define MOL_E2_SHARE 0
+#endif
+// the last MOL_E2_SHARE (0, 1 or 2) 16-unit chunks of E2 are converted by the slot's E3 warpgroup, after its E3 of the
+// previous query (that group idles ~0.8k clk per query waiting for the E1/E2 group, which is the longer chain:
+// profiles/r01_trace_slot0.log).  e2_done then collects both groups.  Not yet measured on the GPU.
+constexpr int kE2Share = MOL_E2_SHARE;
+static_assert(kE2Share >= 0 && kE2Share <= 2, "MOL_E2_SHARE must be 0, 1 or 2");
+
 // TMEM column map of one slot (256 columns)
 constexpr uint32_t kColLog = 0;     // LOG fp32 [0, L); A2 fp16 aliases [0, L/2) + ones [L/2, L/2 + 8)
 constexpr uint32_t kColHid = 64;    // HID fp32 [64, 192); A3 fp16 aliases [64, 128) + ones [128, 136)
@@ -295,6 +304,46 @@ struct SlotSeq {
   }
 };
 
+// One 16-unit chunk of E2: u = 16 fp32 HID values of this thread's item -> h = silu(2u) = u + u tanh(u) as 8 packed fp16 pairs,
+// stored to the A3 columns at `taddr`.  bit j2 of `poly`: pair j2 takes tanh from the fp32 polynomial (FMA pipe) instead of
+// MUFU.TANH; h2: the whole chunk uses the MUFU-free half2 form.
+__device__ __forceinline__ void e2_act_chunk(const uint32_t* v, uint32_t taddr, unsigned poly, bool h2) {
+  uint32_t hk[8];
+#pragma unroll
+  for (int j2 = 0; j2 < 8; ++j2) {
+    if (h2) {  // whole chunk MUFU-free in packed half2 (MOL_E2_H2_MASK)
+      hk[j2] = silu2_h2(pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1])));
+    } else if ((poly >> j2) & 1u) {
+      const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+      const float2 c = make_float2(clamp_sym(u.x, kTanhC), clamp_sym(u.y, kTanhC));
+      const float2 s2 = __fmul2_rn(c, c);
+#if MOL_E2_POLY_DEG == 6
+      float2 p = __ffma2_rn(make_float2(kT6, kT6), s2, make_float2(kT5, kT5));
+#else
+      float2 p = __ffma2_rn(make_float2(kT8, kT8), s2, make_float2(kT7, kT7));
+      p = __ffma2_rn(p, s2, make_float2(kT6, kT6));
+      p = __ffma2_rn(p, s2, make_float2(kT5, kT5));
+#endif
+      p = __ffma2_rn(p, s2, make_float2(kT4, kT4));
+      p = __ffma2_rn(p, s2, make_float2(kT3, kT3));
+      p = __ffma2_rn(p, s2, make_float2(kT2, kT2));
+      p = __ffma2_rn(p, s2, make_float2(kT1, kT1));
+      p = __ffma2_rn(p, s2, make_float2(kT0, kT0));
+      const float2 t = __fmul2_rn(c, p);
+      const float2 h = __ffma2_rn(u, t, u);
+      hk[j2] = pack_f16x2(h.x, h.y);
+    } else {
+      const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
+#ifdef MOL_ABLATE_E2
+      hk[j2] = fma_f16x2(u2, u2, u2);
+#else
+      hk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
+#endif
+    }
+  }
+  tmem_st_x8(taddr, hk);
+}
+
 template <int PX, int DD>
 __global__ void __launch_bounds__(kThreads, 1)
 mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmGI,
@@ -327,7 +376,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_init(&bars->e1_done[s], 128);
       mbar_init(&bars->a2_read[s], 128);
       mbar_init(&bars->e2a_done[s], 128);
-      mbar_init(&bars->e2_done[s], 128);
+      mbar_init(&bars->e2_done[s], kE2Share > 0 ? 256 : 128);
       mbar_init(&bars->gate_free[s], 128);
       mbar_init(&bars->log_full[s], 1);
       mbar_init(&bars->hid_full[s], 1);
@@ -648,53 +697,25 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (warp == 4) TR(1, 1, cnt);
       uint32_t va[16], vb[16];
       auto act = [&](const uint32_t* v, uint32_t col, unsigned poly, bool h2) __attribute__((always_inline)) {
-        uint32_t hk[8];  // bit j2 of `poly`: pair j2 of this chunk takes tanh from the polynomial (FMA pipe), else MUFU.TANH
-#pragma unroll
-        for (int j2 = 0; j2 < 8; ++j2) {
-          if (h2) {  // whole chunk MUFU-free in packed half2 (MOL_E2_H2_MASK)
-            hk[j2] = silu2_h2(pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1])));
-          } else if ((poly >> j2) & 1u) {
-            const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
-            const float2 c = make_float2(clamp_sym(u.x, kTanhC), clamp_sym(u.y, kTanhC));
-            const float2 s2 = __fmul2_rn(c, c);
-#if MOL_E2_POLY_DEG == 6
-            float2 p = __ffma2_rn(make_float2(kT6, kT6), s2, make_float2(kT5, kT5));
-#else
-            float2 p = __ffma2_rn(make_float2(kT8, kT8), s2, make_float2(kT7, kT7));
-            p = __ffma2_rn(p, s2, make_float2(kT6, kT6));
-            p = __ffma2_rn(p, s2, make_float2(kT5, kT5));
-#endif
-            p = __ffma2_rn(p, s2, make_float2(kT4, kT4));
-            p = __ffma2_rn(p, s2, make_float2(kT3, kT3));
-            p = __ffma2_rn(p, s2, make_float2(kT2, kT2));
-            p = __ffma2_rn(p, s2, make_float2(kT1, kT1));
-            p = __ffma2_rn(p, s2, make_float2(kT0, kT0));
-            const float2 t = __fmul2_rn(c, p);
-            const float2 h = __ffma2_rn(u, t, u);
-            hk[j2] = pack_f16x2(h.x, h.y);
-          } else {
-            const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
-#ifdef MOL_ABLATE_E2
-            hk[j2] = fma_f16x2(u2, u2, u2);
-#else
-            hk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
-#endif
-          }
-        }
-        tmem_st_x8(base + col, hk);
+        e2_act_chunk(v, base + col, poly, h2);
       };
       // 8 chunks of 16 hidden units, loads one chunk ahead; A3 chunk c (8 columns) overwrites HID columns that
       // chunk c/2 (already in registers) came from
+      constexpr int nE2 = 8 - kE2Share;  // chunks [nE2, 8) are converted by the slot's E3 warpgroup (MOL_E2_SHARE)
       tmem_ld_x16(base + kColHid, va);
 #pragma unroll
       for (int c = 0; c < 8; c += 2) {
-        tmem_ld_wait_bind16(va);
-        tmem_ld_x16(base + kColHid + 16 * (c + 1), vb);
-        act(va, kColHid + 8 * c, (unsigned)((kE2Poly64 >> (8 * c)) & 0xffull), ((kE2H2Mask >> c) & 1u) != 0);
-        tmem_ld_wait_bind16(vb);
-        if (c + 2 < 8) tmem_ld_x16(base + kColHid + 16 * (c + 2), va);
-        act(vb, kColHid + 8 * (c + 1), (unsigned)((kE2Poly64 >> (8 * (c + 1))) & 0xffull),
-            ((kE2H2Mask >> (c + 1)) & 1u) != 0);
+        if (c < nE2) {
+          tmem_ld_wait_bind16(va);
+          if (c + 1 < nE2) tmem_ld_x16(base + kColHid + 16 * (c + 1), vb);
+          act(va, kColHid + 8 * c, (unsigned)((kE2Poly64 >> (8 * c)) & 0xffull), ((kE2H2Mask >> c) & 1u) != 0);
+          if (c + 1 < nE2) {
+            tmem_ld_wait_bind16(vb);
+            if (c + 2 < nE2) tmem_ld_x16(base + kColHid + 16 * (c + 2), va);
+            act(vb, kColHid + 8 * (c + 1), (unsigned)((kE2Poly64 >> (8 * (c + 1))) & 0xffull),
+                ((kE2H2Mask >> (c + 1)) & 1u) != 0);
+          }
+        }
         if (c == 2) {  // first half of A3 (k < 64) is in TMEM: the issuer may start G3
           tmem_st_wait();
           tc_fence_before();
@@ -917,6 +938,29 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     };
 
+    // MOL_E2_SHARE: the last kE2Share chunks of E2 of the slot's current query (E1 index `cnt`), converted by this group.
+    // Their A3 columns alias the fp32 HID columns of chunk 3, which the E1/E2 group has loaded once e2a_done fires.
+    // (hid_full / e2a_done cannot run a phase ahead of this wait: G2 of the next query is issued behind e2_done of this
+    // one, which needs this group's arrival.)
+    auto e2_share = [&]() __attribute__((always_inline)) {
+      if constexpr (kE2Share > 0) {
+        mbar_wait_sleep(&bars->hid_full[wg], cnt & 1u);
+        mbar_wait_sleep(&bars->e2a_done[wg], cnt & 1u);
+        tc_fence_after();
+        uint32_t hv[16];
+#pragma unroll
+        for (int c = 8 - kE2Share; c < 8; ++c) {
+          tmem_ld_x16(base + kColHid + 16 * c, hv);
+          tmem_ld_wait_bind16(hv);
+          e2_act_chunk(hv, base + kColHid + 8 * c, (unsigned)((kE2Poly64 >> (8 * c)) & 0xffull),
+                       ((kE2H2Mask >> c) & 1u) != 0);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars->e2_done[wg]);
+      }
+    };
+
     uint32_t pkA[L / 2], pkB[L / 2];
     int tile_p = 0, q_p = 0;
     bool have_p = false;
@@ -934,6 +978,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         e3(pk_prev, tile_p, q_p, (cnt - 1u) & 1u, true);
         if (have_n) load_gq(q_n);  // gq(next), staged by the next step's E3
       }
+      e2_share();  // (no-op unless MOL_E2_SHARE)
       ++cnt;
       tile_p = tile;
       q_p = q;
@@ -1662,7 +1707,7 @@ static void* g_trace = nullptr;
 #define MOL_STR(x) MOL_STR2(x)
 const char* coarse_build_knobs() {
   return "e2poly=" MOL_STR(MOL_E2_POLY_MASK) " e2h2=" MOL_STR(MOL_E2_H2_MASK) " e3poly=" MOL_STR(MOL_E3_POLY_OF4)
-         " e3h2=" MOL_STR(MOL_E3_H2_OF4) " h2lite=" MOL_STR(MOL_H2_LITE) " ex2emu=" MOL_STR(MOL_EX2_EMU_OF4);
+         " e3h2=" MOL_STR(MOL_E3_H2_OF4) " h2lite=" MOL_STR(MOL_H2_LITE) " ex2emu=" MOL_STR(MOL_EX2_EMU_OF4) " e2share=" MOL_STR(MOL_E2_SHARE);
 }
 
 void* coarse_trace_buffer() { return g_trace; }
