@@ -32,6 +32,15 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert b"sm_100a" in lib.mol_version()
 
 
+def test_default_build_reports_the_shipped_kernel_knobs():
+    """The in-tree library is the shipped configuration: the experimental activation / sharing knobs are off (tuning
+    variants are separate files selected with MOL_B200_LIB and report their own knobs)."""
+    if os.environ.get("MOL_B200_LIB"):
+        pytest.skip("a tuning variant is loaded")
+    k = _lib.build_knobs()
+    assert k == {"e2poly": 0x0E, "e2h2": 0, "e3poly": 0, "e3h2": 0, "h2lite": 0, "ex2emu": 0, "e2share": 0}
+
+
 def test_constants_match_header():
     h = _header()
     assert int(re.search(r"#define MOL_MAX_K (\d+)", h).group(1)) == _lib.MOL_MAX_K
