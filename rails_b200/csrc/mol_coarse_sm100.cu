@@ -66,6 +66,12 @@ constexpr int kEx2EmuOf4 = MOL_EX2_EMU_OF4;
 #define MOL_G1_SPLIT 0  // measured: 35.5 ms split vs 34.4 ms unsplit per 512 x 1M step
 #endif
 constexpr bool kG1Split = MOL_G1_SPLIT != 0;
+#ifndef MOL_G1_LATE
+#define MOL_G1_LATE 0  // not yet measured
+#endif
+// the next query's G1 (790 clk of tensor pipe, result not needed before this query's E2 ends) is issued behind G3's first
+// part instead of directly behind G2, so it does not sit in front of the other slot's latency-critical G2 / G3
+constexpr bool kG1Late = MOL_G1_LATE != 0;
 #ifndef MOL_E1_EARLY
 #define MOL_E1_EARLY 0  // measured: 35.6 ms early vs 34.6 ms at the loop top per 512 x 1M step
 #endif
@@ -77,6 +83,7 @@ constexpr bool kE1Early = MOL_E1_EARLY != 0;
 // second MMA skips the 4 KB shared-memory fetch of A: 26.6 instead of 39.9 clk per MMA)
 constexpr bool kG1Pair = MOL_G1_PAIR != 0;
 static_assert(!(kG1Pair && kG1Split), "MOL_G1_PAIR and MOL_G1_SPLIT are exclusive");
+static_assert(!(kG1Late && (kG1Split || kG1Pair)), "MOL_G1_LATE excludes MOL_G1_SPLIT / MOL_G1_PAIR");
 #ifndef MOL_E2_POLY_MASK
 #define MOL_E2_POLY_MASK 0x0E
 #endif
@@ -573,7 +580,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               g1_stage = sn;
               pre_g1 = true;
             }
-            if (g1_stage >= 0) do_g1(g1_stage, g1_stage == s && j + 1 < n ? j + 1 : 0, j + 1 < n ? w.n_mine(1) : wn.n_mine(1), kG1Split ? 0 : 2);
+            if (g1_stage >= 0 && !kG1Late) do_g1(g1_stage, g1_stage == s && j + 1 < n ? j + 1 : 0, j + 1 < n ? w.n_mine(1) : wn.n_mine(1), kG1Split ? 0 : 2);
             if (wg == 0) TR(2, 2, c2);
             // ---- G3, first part: needs the first half of A3 (E2), the diag of this query staged and GATE released
             //      by E3 of the previous query (gate_free; its first phase is arrived by the E1/E3 group's prologue)
@@ -603,6 +610,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
             __syncwarp();
             if (kG1Split && g1_stage >= 0) issue_g1(g1_stage, 1);
+            if (kG1Late && g1_stage >= 0) issue_g1(g1_stage, 2);
             if (wg == 0) TR(2, 4, c2);
             // ---- G3, second part, once E2 has written all of A3
             mbar_wait_sleep(&bars->e2_done[wg], c2 & 1u);
@@ -1707,7 +1715,8 @@ static void* g_trace = nullptr;
 #define MOL_STR(x) MOL_STR2(x)
 const char* coarse_build_knobs() {
   return "e2poly=" MOL_STR(MOL_E2_POLY_MASK) " e2h2=" MOL_STR(MOL_E2_H2_MASK) " e3poly=" MOL_STR(MOL_E3_POLY_OF4)
-         " e3h2=" MOL_STR(MOL_E3_H2_OF4) " h2lite=" MOL_STR(MOL_H2_LITE) " ex2emu=" MOL_STR(MOL_EX2_EMU_OF4) " e2share=" MOL_STR(MOL_E2_SHARE);
+         " e3h2=" MOL_STR(MOL_E3_H2_OF4) " h2lite=" MOL_STR(MOL_H2_LITE) " ex2emu=" MOL_STR(MOL_EX2_EMU_OF4)
+         " e2share=" MOL_STR(MOL_E2_SHARE) " g1late=" MOL_STR(MOL_G1_LATE);
 }
 
 void* coarse_trace_buffer() { return g_trace; }

@@ -11,6 +11,8 @@ VARIANTS=(
   "h2_3c MOL_E2_H2_MASK=0x3C MOL_E2_POLY_MASK=0"
   "h2_7e MOL_E2_H2_MASK=0x7E MOL_E2_POLY_MASK=0"
   "h2_3f MOL_E2_H2_MASK=0x3F MOL_E2_POLY_MASK=0"
+  "g1late MOL_G1_LATE=1"                                # next query's G1 issued behind G3a instead of behind G2 (unmeasured)
+  "g1late_h2_3e MOL_G1_LATE=1 MOL_E2_H2_MASK=0x3E MOL_E2_POLY_MASK=0"
   "sh1 MOL_E2_SHARE=1"                                  # E3 group converts E2's last chunk (unmeasured)
   "sh2 MOL_E2_SHARE=2"
   "sh1_h2_3e MOL_E2_SHARE=1 MOL_E2_H2_MASK=0x3E MOL_E2_POLY_MASK=0"
