@@ -361,6 +361,7 @@ def main():
                 "workload": workload_name(args), "parallelism": f"corpus-sharded x{world}" if world > 1 else "single GPU",
                 "mode": args.mode, "tensor_path": bool(tensor_path),
                 "l2_policy": "inputs larger than L2 (fp16 index: 640 MB per full corpus pass)",
+                "library": lib.mol_version().decode(),  # build knobs of the loaded libmol_b200 (tuning variants differ)
             },
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline,
