@@ -17,6 +17,7 @@ VARIANTS=(
   "sh2 MOL_E2_SHARE=2"
   "sh1_h2_3e MOL_E2_SHARE=1 MOL_E2_H2_MASK=0x3E MOL_E2_POLY_MASK=0"
   "sh1_h2_be MOL_E2_SHARE=1 MOL_E2_H2_MASK=0xBE MOL_E2_POLY_MASK=0"  # the shared chunk (7) MUFU-free as well
+  "all3 MOL_G1_LATE=1 MOL_E2_SHARE=1 MOL_E2_H2_MASK=0x3E MOL_E2_POLY_MASK=0"
 )
 CANDIDATES=${CANDIDATES:-"h2_3e sh1_h2_3e"}
 cd "$(dirname "$0")/.."
