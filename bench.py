@@ -2,20 +2,24 @@
 """bench.py — MoL brute-force top-k queries/s (BASELINE.json metric) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config north|cfg1|cfg2|cfg3|cfg4|cfg5] [--items N --batch B --k K]
+                    [--parallelism auto|replicate|shard]
 
-Workload (north star): synthetic MoL 8x8x32 (d=32, D=64, H=128, tau=0.05), top-100 over a 1M-item
+Default workload (north star): synthetic MoL 8x8x32 (d=32, D=64, H=128, tau=0.05), top-100 over a 1M-item
 corpus, batch of 512 queries per step.  A "step" is one MoLBruteForceTopK.forward over the batch.
-With N>1 the corpus is sharded by contiguous item range over the ranks (strong scaling), each rank
-searches its shard, and one NCCL all-gather + a GPU merge produce the global top-k on every rank.
+With N>1 there are two layouts (rails_b200/indexing/sharded_top_k.py), both with ONE all-gather on the data path:
+  replicate: every rank holds the corpus and searches its slice of the query batch (corpora that fit one GPU);
+  shard:     every rank holds a contiguous item range, per-shard top-k lists are merged (BASELINE configs 4, 5).
 
-One JSON line on rank 0:  value = whole-job queries/s with inputs resident in HBM; e2e = the same
-through the C-ABI host entry (pinned host queries in, scores/ids out, copies inside the timed region);
-roofline = the dominant scoring kernel against MEASURED_PEAKS.json; cpu_baseline = the CPU oracle
-(port of the reference's PyTorch path) timed on this box's host cores on a bounded sample.
+One JSON line on rank 0:  value = whole-job queries/s with inputs resident in HBM; e2e = the same through the
+host entry (pinned host queries in, scores/ids out, copies inside the timed region); roofline = the dominant scoring
+kernel against MEASURED_PEAKS.json; cpu_baseline = the CPU oracle (port of the reference's PyTorch path) timed on this
+box's host cores on a bounded sample, and the same sample is used to CHECK the GPU result (`parity`).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -39,25 +43,38 @@ def parse():
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--items", type=int, default=1_000_000)
-    p.add_argument("--batch", type=int, default=512)
-    p.add_argument("--k", type=int, default=100)
+    p.add_argument("--config", default="north", choices=["north", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    p.add_argument("--items", type=int, default=None)
+    p.add_argument("--batch", type=int, default=None)
+    p.add_argument("--k", type=int, default=None)
     p.add_argument("--mode", default="auto", choices=["auto", "exact", "tensor"])
-    p.add_argument("--cpu-queries", type=int, default=32, help="queries in the cpu_baseline sample (~11 s of CPU work)")
+    p.add_argument("--parallelism", default="auto", choices=["auto", "replicate", "shard"])
+    p.add_argument("--cpu-queries", type=int, default=32, help="queries in the cpu_baseline / parity sample (~11 s of CPU work)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-secondary", action="store_true", help="skip the secondary configs / batch sweep block")
+    p.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-this-GPU baseline leg")
     return p.parse_args()
 
 
-def workload_cfg():
-    from oracle.mol_oracle import MoLConfig
+# ---------------------------------------------------------------------------------------------- workloads
+def workload(name, args):
+    """(cfg, N, B, k, fixture or None, label) of a BASELINE.json config."""
+    from rails_b200.workloads import CFG_8x8x32, CFG_16x16x64, MoLConfig
 
-    return MoLConfig(64, 64, 32, 8, 8, 0.05, "geglu", ())
+    if name == "cfg1":  # real ML-1M checkpoint + item table (tests/golden/cfg1_ml1m_ckpt.npz), batch 1
+        from tests.golden_util import load_golden
 
-
-def workload_name(args):
-    return (
-        f"synthetic MoL 8x8x32 d=32 D=64 H=128, top-{args.k} over {args.items} items, batch={args.batch}"
-    )
+        g = load_golden("cfg1_ml1m_ckpt")
+        return g["cfg"], g["items"].size(0), 1, 10, g, "ML-1M HSTU+MoL 8x4x64 ckpt"
+    table = {
+        "north": (CFG_8x8x32, 1_000_000, 512, 100, "synthetic MoL 8x8x32 d=32 D=64 H=128"),
+        "cfg2": (MoLConfig(256, 256, 128, 8, 4, 0.05, "swiglu", (16384,)), 27_278, 128, 100, "ML-20M MoL 8x4x128 (synthetic weights)"),
+        "cfg3": (CFG_8x8x32, 695_762, 256, 200, "Amazon-Books MoL 8x8x32 (synthetic weights)"),
+        "cfg4": (CFG_8x8x32, 10_000_000, 512, 100, "synthetic MoL 8x8x32 d=32"),
+        "cfg5": (CFG_16x16x64, 100_000_000, 1024, 100, "synthetic MoL 16x16x64 d=64"),
+    }
+    cfg, N, B, k, label = table[name]
+    return cfg, N, B, k, None, label
 
 
 def flops_per_pair(cfg):
@@ -66,7 +83,7 @@ def flops_per_pair(cfg):
 
 
 def bytes_per_item(cfg):
-    return 2 * (cfg.item_dot_product_groups * cfg.dot_product_dimension + cfg.num_logits)  # bf16 X_sub + GI
+    return 2 * (cfg.item_dot_product_groups * cfg.dot_product_dimension + cfg.num_logits)  # 16-bit X_sub + GI
 
 
 def peaks():
@@ -133,19 +150,51 @@ class ClockSampler:
         }
 
 
-def cpu_oracle_time(cfg, sd, items_cpu, ids_cpu, queries_cpu, k, reps=1):
-    """Times the CPU oracle (oracle/mol_oracle.py, the port of the reference's PyTorch path) with all host threads."""
+# ---------------------------------------------------------------------------------------------- baselines (the checker)
+def cpu_oracle_run(cfg, sd, items_cpu, ids_cpu, queries_cpu, k, user_ids=None, chunk=2):
+    """Runs the CPU oracle (oracle/mol_oracle.py, the port of the reference's PyTorch path) with all host threads.
+    Returns (seconds, top scores, top ids, all scores)."""
     from oracle import mol_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
-    best = None
     with torch.inference_mode():
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            O.brute_force_top_k(cfg, sd, queries_cpu, items_cpu, ids_cpu, k, chunk=2)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    return best
+        t0 = time.perf_counter()
+        s, i, all_scores = O.brute_force_top_k(cfg, sd, queries_cpu, items_cpu, ids_cpu, k, user_ids, chunk=chunk)
+        dt = time.perf_counter() - t0
+    return dt, s, i, all_scores
+
+
+def gpu_eager_baseline(cfg, sd_dev, items, ids, queries, k, nq, chunk=2, reps=3):
+    """The reference's arithmetic as eager PyTorch ON THIS GPU (the oracle's ATen ops issued on CUDA tensors, queries
+    chunked with the reference's user_max_batch_size semantics, data/eval.py:131-138): fp32 with TF32 off, and bf16 as
+    eval_from_checkpoint.py:318-322 casts the model.  A reported baseline, timed with CUDA events."""
+    from oracle import mol_oracle as O
+
+    out = {}
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for name, dtype in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+            q = queries[:nq]
+
+            def run():
+                return O.brute_force_top_k(cfg, sd_dev, q, items, ids, k, None, dtype, chunk=chunk)
+
+            with torch.inference_mode():
+                run()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    run()
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            out[name] = {"value": nq / (ms * 1e-3), "unit": UNIT, "ms_per_sample": ms}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    out["sample"] = f"{nq} queries x the full corpus per run, chunks of {chunk} queries, eager torch CUDA ops, TF32 off"
+    return out
 
 
 def run_reference(args):
@@ -154,31 +203,39 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = workload_cfg()
-    from tests.helpers import build_module, synthetic_inputs
+    from rails_b200.workloads import build_module, synthetic_inputs
 
-    mol, _ = build_module(cfg, None, "cpu", seed=0)
-    sd = {k: v.detach() for k, v in mol.state_dict().items()}
+    cfg, N, B, k, fixture, label = workload(args.config, args)
+    N, B, k = args.items or N, args.batch or B, args.k or k
+    mol, _ = build_module(cfg, None if fixture is None else fixture["sd"], "cpu", seed=0)
+    sd = {kk: v.detach() for kk, v in mol.state_dict().items()}
     # exactly --steps K timed steps after --warmup W; the sample per step (queries against the full corpus) shrinks with
-    # K + W so that the run stays within a few minutes (~0.34 s of CPU per query on 16 cores)
+    # K + W so that the run stays within a few minutes (~0.34 s of CPU per query on 16 cores at 1M items)
     steps, warm = max(1, args.steps), max(0, args.warmup)
-    nq = max(1, min(8, 240 // (steps + warm)))
-    items, ids, q, _ = synthetic_inputs(cfg, args.items, nq, 0, "cpu")
+    budget = max(1, int(240e6 / max(N, 1)))  # queries affordable in total
+    nq = max(1, min(8, B, budget // (steps + warm)))
+    Ncpu = min(N, 2_000_000)  # (cfg4 / cfg5: a capped corpus, throughput in pairs/s is what extrapolates)
+    if fixture is None:
+        items, ids, q, uid = synthetic_inputs(cfg, Ncpu, nq, 0, "cpu")
+    else:
+        items, ids, q, uid = fixture["items"], fixture["item_ids"], fixture["queries"][:nq], fixture["user_ids"][:nq]
     for _ in range(warm):
-        cpu_oracle_time(cfg, sd, items, ids, q, args.k)
+        cpu_oracle_run(cfg, sd, items, ids, q, k, uid)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_oracle_time(cfg, sd, items, ids, q, args.k)
+        cpu_oracle_run(cfg, sd, items, ids, q, k, uid)
     dt = (time.perf_counter() - t0) / steps
-    qps = nq / dt
+    qps = nq / dt * (Ncpu / N)
     cores = torch.get_num_threads()
-    sample = f"{nq} queries x full {args.items}-item corpus per step (chunks of 2 queries), fp32, eager"
+    sample = f"{nq} queries x {Ncpu} items per step (chunks of 2 queries), fp32, eager"
+    if Ncpu != N:
+        sample += f"; queries/s scaled by {Ncpu}/{N} to the full corpus"
     line = {
         "impl": "reference",
         "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample": sample},
+        "config": {"workload": workload_name(label, N, B, k), "sample": sample},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -186,6 +243,59 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def workload_name(label, N, B, k):
+    return f"{label}, top-{k} over {N} items, batch={B}"
+
+
+# ---------------------------------------------------------------------------------------------- secondary block
+def time_search(engine, weights, index, wsp, q, uid, k, mode, steps, warmup):
+    for _ in range(warmup):
+        engine.search(weights, index, wsp, q, uid, k, True, mode)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        engine.search(weights, index, wsp, q, uid, k, True, mode)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def secondary_block(dev, mode, north=None):
+    """BASELINE.json configs 1-3 and the B sweep of SURVEY.md §8(d) (1M items, top-100), a few timed steps each."""
+    from rails_b200 import engine
+    from rails_b200.indexing.mol_top_k import MoLBruteForceTopK
+    from rails_b200.workloads import build_module, synthetic_inputs
+
+    out = {}
+    for name in ("cfg1", "cfg2", "cfg3"):
+        cfg, N, B, k, fixture, label = workload(name, None)
+        mol, _ = build_module(cfg, None if fixture is None else fixture["sd"], dev, seed=0)
+        if fixture is None:
+            items, ids, q, uid = synthetic_inputs(cfg, N, B, 0, dev)
+        else:
+            items, ids = fixture["items"].to(dev), fixture["item_ids"].to(dev)
+            q, uid = fixture["queries"][:B].to(dev), fixture["user_ids"][:B].to(dev)
+        top = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=mode)
+        ms = time_search(engine, mol.packed_weights(dev), top._ensure_index(), mol.workspace(dev), q, uid, k, mode, 20, 5)
+        out[name] = {"workload": workload_name(label, N, B, k), "ms_per_step": ms, "queries_per_s": B / (ms * 1e-3),
+                     "tflops_algorithmic": B * N * flops_per_pair(cfg) / (ms * 1e-3) / 1e12,
+                     "hbm_gbs_algorithmic": N * bytes_per_item(cfg) / (ms * 1e-3) / 1e9}
+        del top, items
+    if north is not None:
+        weights, index, wsp, q_dev, k = north
+        sweep = {}
+        for b in (1, 8, 32, 128, 512):
+            if b > q_dev.size(0):
+                continue
+            ms = time_search(engine, weights, index, wsp, q_dev[:b].contiguous(), None, k, mode, 10 if b >= 128 else 30, 3)
+            sweep[str(b)] = {"ms_per_step": ms, "queries_per_s": b / (ms * 1e-3),
+                             "hbm_gbs_algorithmic": index.N * 640 / (ms * 1e-3) / 1e9}
+        out["batch_sweep_1m_top100"] = sweep
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- main arm
 def main():
     args = parse()
     if args.impl == "reference":
@@ -194,7 +304,7 @@ def main():
 
     from rails_b200 import _lib, engine
     from rails_b200.indexing.mol_top_k import MoLBruteForceTopK
-    from tests.helpers import build_module
+    from rails_b200.workloads import build_module
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -212,16 +322,41 @@ def main():
     lib = _lib.load()
     mode = {"auto": _lib.MODE_AUTO, "exact": _lib.MODE_EXACT, "tensor": _lib.MODE_TENSOR}[args.mode]
 
-    cfg = workload_cfg()
-    B, k, N = args.batch, args.k, args.items
-    mol, _ = build_module(cfg, None, dev, seed=0)
-    # corpus shard of this rank: contiguous item range, generated on device
-    lo, hi = rank * N // world, (rank + 1) * N // world
-    g = torch.Generator(device=dev).manual_seed(1 + rank)
-    items = 0.02 * torch.randn(hi - lo, cfg.item_embedding_dim, device=dev, generator=g)
-    ids = torch.arange(lo + 1, hi + 1, dtype=torch.int64, device=dev)
-    gq = torch.Generator().manual_seed(100)
-    q_host = F.layer_norm(torch.randn(B, cfg.query_embedding_dim, generator=gq), (cfg.query_embedding_dim,)).pin_memory()
+    cfg, N, B, k, fixture, label = workload(args.config, args)
+    N, B, k = args.items or N, args.batch or B, args.k or k
+    mol, _ = build_module(cfg, None if fixture is None else fixture["sd"], dev, seed=0)
+    # layout over the ranks: replicate the corpus (query-split) when the whole index fits one GPU, else shard it
+    index_bytes = N * (6 * (cfg.item_dot_product_groups * cfg.dot_product_dimension + cfg.num_logits) + 4 * cfg.item_embedding_dim)
+    layout = args.parallelism
+    if layout == "auto":
+        layout = "shard" if (args.config in ("cfg4", "cfg5") or index_bytes > 40e9) else "replicate"
+    if world == 1:
+        layout = "single"
+
+    def gen_items(lo, hi, seed_rank):
+        g = torch.Generator(device=dev).manual_seed(1 + seed_rank)
+        return 0.02 * torch.randn(hi - lo, cfg.item_embedding_dim, device=dev, generator=g)
+
+    uid_dev = None
+    if fixture is not None:
+        items, ids = fixture["items"].to(dev), fixture["item_ids"].to(dev)
+        q_host = fixture["queries"][:B].contiguous().pin_memory()
+        uid_dev = fixture["user_ids"][:B].to(dev)
+        lo, hi = 0, N
+    else:
+        # corpus (shard) of this rank, generated on device: shard r of an R-way split uses seed 1 + r,
+        # the replicated / single layouts seed 1 for the whole corpus
+        if layout == "shard":
+            lo, hi = rank * N // world, (rank + 1) * N // world
+            items = gen_items(lo, hi, rank)
+        else:
+            lo, hi = 0, N
+            items = gen_items(0, N, 0)
+        ids = torch.arange(lo + 1, hi + 1, dtype=torch.int64, device=dev)
+        gq = torch.Generator().manual_seed(100)
+        q_host = F.layer_norm(torch.randn(B, cfg.query_embedding_dim, generator=gq), (cfg.query_embedding_dim,)).pin_memory()
+        if cfg.uid_embedding_hash_sizes:
+            uid_dev = torch.randint(1, 100000, (B,), generator=gq, dtype=torch.int64).to(dev)
     q_dev = q_host.to(dev)
     top = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=mode)
     index = top._ensure_index()
@@ -229,26 +364,27 @@ def main():
     wsp = mol.workspace(dev)
     out_s_host = torch.empty((B, k), dtype=torch.float32).pin_memory()
     out_i_host = torch.empty((B, k), dtype=torch.int64).pin_memory()
+    uid_host = None if uid_dev is None else uid_dev.cpu().pin_memory()
     tensor_path = engine.tensor_path_supported(weights.shape) and mode != _lib.MODE_EXACT
+    kw = {} if uid_dev is None else {"user_ids": uid_dev}
 
-    sharded = None
+    multi = None
     if world > 1:
-        from rails_b200.indexing.sharded_top_k import ShardedMoLBruteForceTopK
+        from rails_b200.indexing.sharded_top_k import ReplicatedMoLBruteForceTopK, ShardedMoLBruteForceTopK
 
-        # rank-local exact top-k of the shard -> ONE packed all-gather -> (R*k -> k) merge on every rank
-        sharded = ShardedMoLBruteForceTopK(top, hi - lo)
+        multi = ShardedMoLBruteForceTopK(top, hi - lo) if layout == "shard" else ReplicatedMoLBruteForceTopK(top)
 
     def step_device():
         if world == 1:
-            return engine.search(weights, index, wsp, q_dev, None, k, True, mode)
-        return sharded(q_dev, k)
+            return engine.search(weights, index, wsp, q_dev, uid_dev, k, True, mode)
+        return multi(q_dev, k, **kw)
 
     def step_e2e():
         if world == 1:
-            engine.search_host(weights, index, wsp, q_host, None, k, out_s_host, out_i_host, mode)
+            engine.search_host(weights, index, wsp, q_host, uid_host, k, out_s_host, out_i_host, mode)
         else:
             qd = q_host.to(dev, non_blocking=True)
-            s, i = sharded(qd, k)
+            s, i = multi(qd, k, **kw)
             out_s_host.copy_(s, non_blocking=True)
             out_i_host.copy_(i, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -265,30 +401,35 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident throughput
+    # ---- device-resident throughput (no profiling events inside the timed region)
     for _ in range(args.warmup):
-        step_device()
+        res_s, res_i = step_device()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     lib.mol_launch_count_reset()
-    lib.mol_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step_device()
+        res_s, res_i = step_device()
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = int(lib.mol_launch_count())
-    import ctypes
-
-    k_ms, k_n = ctypes.c_double(), ctypes.c_int32()
-    _lib.check(lib.mol_profile_collect(ctypes.byref(k_ms), ctypes.byref(k_n)))
-    lib.mol_profile_enable(0)
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
     value = B / (ms_step * 1e-3)
+    stats = engine.search_stats(wsp)  # counters of the last timed search on this rank
+
+    # ---- the scoring kernel alone: a separate pass with the library's CUDA-event profiling switched on
+    prof_steps = min(args.steps, 3)
+    lib.mol_profile_enable(1)
+    for _ in range(prof_steps):
+        step_device()
+    torch.cuda.synchronize()
+    k_ms, k_n = ctypes.c_double(), ctypes.c_int32()
+    _lib.check(lib.mol_profile_collect(ctypes.byref(k_ms), ctypes.byref(k_n)))
+    lib.mol_profile_enable(0)
 
     # ---- end to end through the host entry (pinned host buffers, copies inside the timed region)
     for _ in range(args.warmup):
@@ -302,24 +443,22 @@ def main():
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e = {
         "value": B / (ms_e2e * 1e-3), "unit": UNIT,
-        "h2d_bytes_per_step": q_host.numel() * 4,
+        "h2d_bytes_per_step": q_host.numel() * 4 + (0 if uid_host is None else uid_host.numel() * 8),
         "d2h_bytes_per_step": out_s_host.numel() * 4 + out_i_host.numel() * 8,
         "ms_per_step": ms_e2e,
     }
+    e2e_ids_equal = bool(torch.equal(out_i_host, res_i.cpu()))
 
-    # ---- roofline of the dominant kernel (scoring pass), this rank's shard
+    # ---- roofline of the dominant kernel (scoring pass) on this rank
     tf_peak, hbm_peak, peak_src = peaks()
     n_local = hi - lo
+    b_local = B if layout != "replicate" else (rank + 1) * B // world - rank * B // world
     # the timed launches are the scoring kernel(s) of every step (tensor path: threshold pass + main pass, which
     # together score each (query, item) pair exactly once); achieved = algorithmic FLOPs / summed launch time
-    kern_ms_step = k_ms.value / args.steps
-    launches_per_step = k_n.value / args.steps
-    flops_step = B * n_local * flops_per_pair(cfg)
+    kern_ms_step = k_ms.value / prof_steps
+    flops_step = b_local * n_local * flops_per_pair(cfg)
     achieved_tf = flops_step / (kern_ms_step * 1e-3) / 1e12 if kern_ms_step > 0 else 0.0
-    if not tensor_path:
-        tf_peak_used, peak_note = tf_peak, peak_src + "; NOTE fp32 CUDA-core kernel measured against the tensor roofline"
-    else:
-        tf_peak_used, peak_note = tf_peak, peak_src
+    peak_note = peak_src if tensor_path else peak_src + "; NOTE fp32 CUDA-core kernel measured against the tensor roofline"
     traffic, traffic_note = None, None
     try:  # measured once under ncu (never inside a timed run): profiles/ncu_traffic.json
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
@@ -331,43 +470,86 @@ def main():
         pass
     roofline = {
         "bound": "tensor", "kernel": "mol_coarse_kernel (tcgen05)" if tensor_path else "exact_scores_kernel(fp32)",
-        "achieved": achieved_tf, "peak": tf_peak_used, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak_used,
+        "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
         "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_note,
-        "kernel_ms_per_step": kern_ms_step, "kernel_launches_per_step": launches_per_step,
+        "kernel_ms_per_step": kern_ms_step, "kernel_launches_per_step": k_n.value / prof_steps,
         "kernel_ms_per_launch": k_ms.value / max(k_n.value, 1),
         "kernel_share_of_step": kern_ms_step / ms_step,
         "hbm_gbs_algorithmic": (n_local * bytes_per_item(cfg)) / (kern_ms_step * 1e-3) / 1e9 if kern_ms_step > 0 else 0.0,
         "hbm_peak_gbs": hbm_peak,
-        "co_limit": "MUFU: 208 transcendentals per pair (H + 2L = 256, minus the 48 hidden-unit tanh the kernel evaluates by polynomial on the FMA pipe) at the measured 16/clk/SM: 23.3 ms per 512 x 1M step at 1.965 GHz; tensor-pipe floor with every MUFU op removed: 22.9 ms",
+        "co_limit": "MUFU (16 transcendentals/clk/SM) and tensor-pipe occupancy of small-N MMAs bind before the FLOP roofline: DESIGN.md section 4.1",
     }
 
-    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload
-    cpu_baseline = None
+    # ---- N > 1: the multi-GPU result must equal the single-GPU result (rank 0, outside every timed region)
+    multi_check = None
+    if world > 1 and rank == 0 and N <= 4_000_000 and fixture is None:
+        if layout == "shard":
+            full_items = torch.cat([gen_items(r * N // world, (r + 1) * N // world, r) for r in range(world)])
+            full_ids = torch.arange(1, N + 1, dtype=torch.int64, device=dev)
+            full = MoLBruteForceTopK(mol, full_items.unsqueeze(0), full_ids.unsqueeze(0), mode=mode)
+            fs, fi = full(q_dev, k, **kw)
+            del full, full_items
+        else:
+            fs, fi = top(q_dev, k, **kw)
+        multi_check = {"ids_equal_single_gpu": bool(torch.equal(fi, res_i)), "scores_equal_single_gpu": bool(torch.equal(fs, res_s)),
+                       "n_queries": B}
+
+    # ---- CPU baseline + parity (rank 0, N=1 only): oracle port on a bounded sample of the same workload; the GPU
+    #      result for those queries is CHECKED against it
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import mol_oracle as O
+
         sd = {kk: v.detach().cpu() for kk, v in mol.state_dict().items()}
-        nq = args.cpu_queries
-        t = cpu_oracle_time(cfg, sd, items.cpu(), ids.cpu(), q_host[:nq].clone(), k)
+        nq = max(1, min(args.cpu_queries, B, int(64e6 // max(N, 1)) or 1))  # ~0.34 s of CPU per query per 1M items
+        ids_cpu = ids.cpu()
+        t, _, _, all_scores = cpu_oracle_run(cfg, sd, items.cpu(), ids_cpu, q_host[:nq].clone(), k,
+                                             None if uid_host is None else uid_host[:nq].clone(), chunk=2 if N <= 2_000_000 else 1)
         cpu_baseline = {
             "value": nq / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{nq} of the {B} queries x the full {N}-item corpus, fp32 eager torch CPU (oracle/mol_oracle.py), {t:.1f} s",
         }
+        r = O.compare_top_k(res_s[:nq], res_i[:nq], all_scores, ids_cpu, k, 1e-3, 1e-4)
+        parity = {
+            "n_queries": nq, "items": N, "strict_id_match": r["strict_row_match"], "tie_aware_ok": r["ok"],
+            "max_score_err": r["max_score_err"], "max_rank_gap": r["max_rank_gap"],
+            "checked_against": "CPU oracle (oracle/mol_oracle.py) over the full corpus, same queries as the timed step",
+        }
+
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager and fixture is None and N <= 4_000_000:
+        sd_dev = {kk: v.detach() for kk, v in mol.state_dict().items()}
+        try:
+            gpu_eager = gpu_eager_baseline(cfg, sd_dev, items, ids, q_dev, k, min(16, B))
+        except torch.cuda.OutOfMemoryError as e:  # (reported, not fatal: it is a baseline leg)
+            gpu_eager = {"error": str(e)[:200]}
+
+    secondary = None
+    if rank == 0 and world == 1 and args.config == "north" and not args.no_secondary and args.items is None and args.batch is None:
+        secondary = secondary_block(dev, mode, (weights, index, wsp, q_dev, k))
 
     if rank == 0:
+        par = {"single": "single GPU", "replicate": f"corpus replicated, queries split x{world}, one all-gather",
+               "shard": f"corpus sharded x{world}, one all-gather + merge"}[layout]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f16" if tensor_path else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f16" if tensor_path else "f32", "data": "synthetic" if fixture is None else "ML-1M checkpoint + synthetic queries",
             "config": {
-                "workload": workload_name(args), "parallelism": f"corpus-sharded x{world}" if world > 1 else "single GPU",
+                "workload": workload_name(label, N, B, k), "parallelism": par,
                 "mode": args.mode, "tensor_path": bool(tensor_path),
-                "l2_policy": "inputs larger than L2 (fp16 index: 640 MB per full corpus pass)",
+                "l2_policy": f"inputs larger than L2 (16-bit index: {n_local * bytes_per_item(cfg) / 1e6:.0f} MB per corpus pass)"
+                if n_local * bytes_per_item(cfg) > 126e6 else "corpus smaller than L2 (latency-bound config; stated, not flushed)",
                 "library": lib.mol_version().decode(),  # build knobs of the loaded libmol_b200 (tuning variants differ)
             },
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
+            "search_stats": stats, "fallback_queries": stats["fallback_queries"], "e2e_ids_equal_device_run": e2e_ids_equal,
+            "parity": parity, "multi_gpu_check": multi_check,
+            "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager, "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

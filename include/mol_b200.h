@@ -78,6 +78,10 @@ typedef struct mol_weights {
   const float* qi_b1;   /* ...1.bias                                          (H)           */
   const float* qi_w2;   /* ...3.weight                                        (L, H)        */
   const float* qi_b2;   /* ...3.bias                                          (L)           */
+  /* Optional: device blob filled by mol_weights_prepare() with the operands that depend on the weights alone (the
+   * transposed qi-MLP matrices of the fp32 kernels, the fp16 operand images of the tensor-core pass).  NULL: every
+   * search call recomputes them inside its workspace (a few small launches). */
+  const void* prepared;
 } mol_weights_t;
 
 /* The item-side cache ("index").  raw_items / item_ids are BORROWED from the caller exactly as
@@ -101,6 +105,12 @@ const char* mol_last_error(void);
  * tcgen05 coarse pass supports it. */
 int mol_shape_check(const mol_shape_t* shape, int32_t* tensor_ok);
 
+/* Weight-derived operands, once per weight version: bytes of the blob / fill it (256-byte aligned device memory), then
+ * point mol_weights_t::prepared at it. */
+int mol_weights_prepared_bytes(const mol_shape_t* shape, size_t* bytes);
+int mol_weights_prepare(const mol_shape_t* shape, const mol_weights_t* w, void* blob, size_t blob_bytes,
+                        mol_stream_t stream);
+
 /* Bytes of the cache blob for N items. */
 int mol_index_bytes(const mol_shape_t* shape, int64_t num_items, size_t* bytes);
 /* Carves `blob` into the four caches and fills *index (no device work). */
@@ -123,6 +133,12 @@ int mol_search(const mol_shape_t* shape, const mol_weights_t* w, const mol_index
                const float* queries, const int64_t* user_ids, int32_t B, int32_t k, int32_t sorted,
                int32_t mode, float* out_scores, int64_t* out_ids, void* workspace,
                size_t workspace_bytes, mol_stream_t stream);
+
+/* Counters of the LAST mol_search / mol_search_host call that used `workspace` (8 x int32, copied to host_stats; this
+ * call synchronises the stream): [0] queries re-done by the exact fallback, [1] queries whose candidate filter
+ * overflowed, [2] largest survivor count of a query, [3] 1 if the fused-filter strategy ran, [4] 1 if the tensor-core
+ * path ran, [5] queries with fewer than K' survivors, [6] K', [7] survivor capacity per query. */
+int mol_search_stats(const void* workspace, int32_t* host_stats, mol_stream_t stream);
 
 /* Same call with HOST buffers for queries / user_ids / outputs (pinned memory recommended): copies
  * in, searches, copies out and synchronises the stream.  Device staging lives in the workspace
@@ -154,6 +170,17 @@ int mol_merge_topk_workspace_bytes(int32_t R, int32_t B, int32_t k, size_t* byte
 int mol_merge_topk(const float* part_scores, const int64_t* part_ids, int32_t R, int32_t B,
                    int32_t k, float* out_scores, int64_t* out_ids, void* workspace,
                    size_t workspace_bytes, mol_stream_t stream);
+
+/* The same exchange with ONE buffer per rank: mol_pack_topk packs a rank's (B, k_valid) partial list (k_valid <= k; the
+ * remaining k - k_valid entries of each row are marked invalid - a shard with fewer than k items) into (B, k) entries of
+ * MOL_PACKED_ENTRY_BYTES {int64 id, float score, int32 valid}; after a single all-gather, mol_merge_topk_packed reads the
+ * gathered (R, B, k) entries and writes the global (B, k).  Ids may be any int64 (validity is explicit). */
+#define MOL_PACKED_ENTRY_BYTES 16
+int mol_pack_topk(const float* scores, const int64_t* ids, int32_t B, int32_t k_valid, int32_t k, void* out_packed,
+                  mol_stream_t stream);
+int mol_merge_topk_packed_workspace_bytes(int32_t R, int32_t B, int32_t k, size_t* bytes);
+int mol_merge_topk_packed(const void* gathered, int32_t R, int32_t B, int32_t k, float* out_scores, int64_t* out_ids,
+                          void* workspace, size_t workspace_bytes, mol_stream_t stream);
 
 /* Generic row-wise top-k of a device score matrix (B rows, n columns, row stride ld): the
  * replacement of torch.topk(dim=1, largest=True, sorted=True) at mol_top_k.py:123-129.

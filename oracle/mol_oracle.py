@@ -26,42 +26,13 @@ State-dict key names are those of ``MoLSimilarity`` built by
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.nn.functional as F
 
 
-@dataclass
-class MoLConfig:
-    """Shape/hyper-parameters of one MoL head (names follow the reference's ctor kwargs)."""
-
-    query_embedding_dim: int
-    item_embedding_dim: int
-    dot_product_dimension: int
-    query_dot_product_groups: int
-    item_dot_product_groups: int
-    temperature: float = 0.05
-    query_nonlinearity: str = "geglu"  # "geglu" | "swiglu"
-    uid_embedding_hash_sizes: Tuple[int, ...] = ()
-    softmax_dropout_rate: float = 0.2
-    eps: float = 1e-6
-
-    @property
-    def num_logits(self) -> int:
-        return self.query_dot_product_groups * self.item_dot_product_groups
-
-    def to_json(self) -> dict:
-        d = dict(self.__dict__)
-        d["uid_embedding_hash_sizes"] = list(self.uid_embedding_hash_sizes)
-        return d
-
-    @staticmethod
-    def from_json(d: dict) -> "MoLConfig":
-        d = dict(d)
-        d["uid_embedding_hash_sizes"] = tuple(d.get("uid_embedding_hash_sizes", ()))
-        return MoLConfig(**d)
+from rails_b200.workloads import MoLConfig  # noqa: E402,F401  (shape dataclass; pure Python, no CUDA library)
 
 
 # state-dict keys (reference MoLSimilarity; SURVEY.md §8a "Weights of the path")

@@ -1,7 +1,7 @@
 """Imports the UNMODIFIED reference from /root/reference (build container only).
 
 TEST INFRASTRUCTURE.  Used by ``oracle/gen_golden.py`` to produce ``tests/golden/*.npz`` and by
-``tests/test_oracle_vs_reference.py`` (skipped when /root/reference is absent, e.g. on the GPU box).
+``oracle/gen_golden_large.py`` / ``oracle/gen_golden_next.py`` (build container only: /root/reference is absent on the GPU box).
 The reference's ``modeling/similarity_utils.py`` imports ``gin`` (not installed): a stub whose
 ``configurable`` is the identity decorator is put on ``sys.modules`` first, then
 ``create_mol_interaction_module`` is called with explicit kwargs taken from the .gin files
@@ -42,12 +42,20 @@ def import_reference():
     if not reference_available():
         raise RuntimeError(f"reference not found at {REFERENCE_ROOT}")
     _install_gin_stub()
-    if REFERENCE_ROOT not in sys.path:
+    # this repo ships a `rails` ALIAS package (rails/__init__.py -> rails_b200): it must never stand in for the reference
+    # here.  Drop any alias modules already imported, put the reference first on sys.path, and verify what was imported.
+    for name in [m for m in sys.modules if m == "rails" or m.startswith("rails.")]:
+        if not (getattr(sys.modules[name], "__file__", None) or "").startswith(REFERENCE_ROOT):
+            del sys.modules[name]
+    if sys.path[0] != REFERENCE_ROOT:
         sys.path.insert(0, REFERENCE_ROOT)
     import modeling.similarity_utils as su  # noqa: E402
-    from rails.indexing.mol_top_k import MoLBruteForceTopK  # noqa: E402
+    import rails.indexing.mol_top_k as ref_top_k  # noqa: E402
 
-    return su, MoLBruteForceTopK
+    for mod in (su, ref_top_k):
+        if not os.path.abspath(mod.__file__).startswith(os.path.abspath(REFERENCE_ROOT)):
+            raise RuntimeError(f"{mod.__name__} was imported from {mod.__file__}, not from the reference")
+    return su, ref_top_k.MoLBruteForceTopK
 
 
 def build_reference_mol(cfg) -> "torch.nn.Module":

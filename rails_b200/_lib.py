@@ -33,7 +33,13 @@ EXPORTED_SYMBOLS = (
     "mol_profile_enable", "mol_profile_collect", "mol_select_valid", "mol_mips_workspace_bytes", "mol_mips_search",
     "mol_dot_scores", "mol_index_avg_embeddings", "mol_search_avg_workspace_bytes", "mol_search_avg",
     "mol_search_groups_workspace_bytes", "mol_search_groups",
+    "mol_weights_prepared_bytes", "mol_weights_prepare", "mol_search_stats",
+    "mol_pack_topk", "mol_merge_topk_packed_workspace_bytes", "mol_merge_topk_packed",
 )
+MOL_PACKED_ENTRY_BYTES = 16
+NUM_STATS = 8
+STAT_NAMES = ("fallback_queries", "filter_overflows", "max_survivors", "filter_strategy", "tensor_path",
+              "short_queries", "k_prime", "survivor_capacity")
 
 
 class MolShape(ctypes.Structure):
@@ -64,6 +70,7 @@ class MolWeights(ctypes.Structure):
         ("gq_w1", c_void_p), ("gq_b1", c_void_p), ("gq_w2", c_void_p),
         ("gi_w1", c_void_p), ("gi_b1", c_void_p), ("gi_w2", c_void_p),
         ("qi_w1", c_void_p), ("qi_b1", c_void_p), ("qi_w2", c_void_p), ("qi_b2", c_void_p),
+        ("prepared", c_void_p),
     ]
 
 
@@ -144,6 +151,12 @@ def load() -> ctypes.CDLL:
         P(MolShape), P(MolWeights), P(MolIndex), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
     ]
+    lib.mol_weights_prepared_bytes.argtypes = [P(MolShape), P(c_size_t)]
+    lib.mol_weights_prepare.argtypes = [P(MolShape), P(MolWeights), c_void_p, c_size_t, c_void_p]
+    lib.mol_search_stats.argtypes = [c_void_p, P(c_int32), c_void_p]
+    lib.mol_pack_topk.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    lib.mol_merge_topk_packed_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, P(c_size_t)]
+    lib.mol_merge_topk_packed.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.mol_profile_enable.argtypes = [c_int32]
     lib.mol_profile_enable.restype = None
     lib.mol_profile_collect.argtypes = [P(ctypes.c_double), P(c_int32)]
@@ -179,5 +192,6 @@ def check(status: int) -> None:
 
 __all__ = [
     "MolShape", "MolWeights", "MolIndex", "load", "check", "build_knobs", "byref", "c_size_t", "c_int32", "c_void_p",
-    "MODE_AUTO", "MODE_EXACT", "MODE_TENSOR", "MOL_MAX_K", "EXPORTED_SYMBOLS", "LIB_PATH",
+    "MODE_AUTO", "MODE_EXACT", "MODE_TENSOR", "MOL_MAX_K", "EXPORTED_SYMBOLS", "LIB_PATH", "MOL_PACKED_ENTRY_BYTES",
+    "NUM_STATS", "STAT_NAMES",
 ]

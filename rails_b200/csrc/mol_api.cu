@@ -8,6 +8,8 @@
 #include <utility>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "mol_coarse.cuh"
 
@@ -104,10 +106,62 @@ static IndexLayout index_layout(const Dims& D, int64_t N) {
 //            `cand_target` items of the whole corpus exceed; the main coarse pass then appends every
 //            (score, item) above the threshold to a per-query buffer inside the scoring kernel's epilogue, so
 //            no score matrix is written or re-read.  Too many / too few survivors are caught by the safety check.
+// Operands derived from the weights alone: the transposed qi-MLP matrices of the fp32 kernels and the fp16 UMMA
+// images of the tensor-core pass.  Either inside the caller's mol_weights_t::prepared blob (mol_weights_prepare, once
+// per weight version) or, when that is NULL, inside the search workspace and recomputed by every call.
+struct Prepared {
+  float *w1t, *w2t;          // (L,H) / (H,L)
+  uint8_t *w1_img, *w2_img;  // nullptr when the shape has no tensor path
+  int32_t* overflow;         // a weight did not fit fp16
+  size_t total;
+};
+static void plan_prepared(const mol_shape_t& s, void* base, size_t cap, Prepared* p) {
+  Dims D = dims_of(s);
+  Arena a(base, cap);
+  p->w1t = a.take<float>((size_t)D.L * D.H);
+  p->w2t = a.take<float>((size_t)D.L * D.H);
+  p->overflow = a.take<int32_t>(1);
+  p->w1_img = p->w2_img = nullptr;
+  if (coarse_supported(s)) {
+    size_t b1, b2;
+    coarse_weight_image_bytes(s, &b1, &b2);
+    p->w1_img = a.take<uint8_t>(b1);
+    p->w2_img = a.take<uint8_t>(b2);
+  }
+  p->total = align_up(a.off, 256);
+}
+static int run_prepare(const mol_shape_t& s, const mol_weights_t& w, const Prepared& p, cudaStream_t st) {
+  Dims D = dims_of(s);
+  MOL_TRY(launch_transpose(w.qi_w1, p.w1t, D.H, D.L, st));  // (H,L) -> (L,H)
+  MOL_TRY(launch_transpose(w.qi_w2, p.w2t, D.L, D.H, st));  // (L,H) -> (H,L)
+  MOL_CUDA(cudaMemsetAsync(p.overflow, 0, sizeof(int32_t), st));
+  if (p.w1_img) MOL_TRY(coarse_prepare_weights(s, w, p.w1_img, p.w2_img, p.overflow, st));
+  return MOL_OK;
+}
+// the caller's prepared blob if there is one, else `local` (filled now)
+static int get_prepared(const mol_shape_t& s, const mol_weights_t& w, const Prepared& local, Prepared* out,
+                        cudaStream_t st) {
+  if (w.prepared) {
+    plan_prepared(s, const_cast<void*>(w.prepared), (size_t)-1, out);
+    return MOL_OK;
+  }
+  *out = local;
+  return run_prepare(s, w, local, st);
+}
+
+struct NvtxRange {  // visible in nsys / ncu --nvtx; a no-op without a profiler attached
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
+constexpr int kNumStats = 8;  // int32 counters at the start of the search workspace (mol_search_stats)
+
 struct SearchWs {
+  int32_t* stats;       // [0] queries re-done exactly, [1] filter overflows, [2] max survivors, [3] filter strategy used,
+                        // [4] tensor path used, [5] queries with fewer than K' survivors, [6] K', [7] survivor capacity
   // query prologue
   float *pre, *h, *proj, *hq, *qsub, *gq;
-  float *w1t, *w2t;
+  Prepared prep;        // workspace-local copy of the weight-derived operands (used when weights->prepared is NULL)
   // host-entry staging
   float* stage_q;
   int64_t* stage_uid;
@@ -126,6 +180,7 @@ struct SearchWs {
   int32_t* fcnt;        // (chunk) survivors per query
   float* fscores;       // (chunk, cap)
   int32_t* fidx;        // (chunk, cap)
+  int32_t *map_sample, *map_main;  // logical -> physical tile tables of the strided sample / its complement
   CoarseWs coarse;
   int chunk;            // queries per chunk
   int chunk_fb;         // queries per exact-fallback sub-chunk
@@ -133,6 +188,7 @@ struct SearchWs {
   int S;                // segments for the (chunk, n) select
   int filter;           // 1 = filter strategy
   int64_t sample;       // sample items (multiple of 128)
+  int samp_stride;      // the sample is every samp_stride-th item tile (1: the first `sample` items)
   int m;                // sample rank that defines the threshold
   int cap;              // survivor capacity per query
   size_t total;
@@ -162,14 +218,19 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
   Dims D = dims_of(s);
   Arena a(base, cap);
   const bool tensor = use_tensor(s, mode);
+  ws->stats = a.take<int32_t>(kNumStats);  // (offset 0 of the workspace: mol_search_stats reads it back)
   ws->pre = a.take<float>((size_t)B * 2 * D.Hq);
   ws->h = a.take<float>((size_t)B * D.Hq);
   ws->proj = a.take<float>((size_t)B * D.Pq_proj * D.d);
   ws->hq = a.take<float>((size_t)B * D.Hgq);
   ws->qsub = a.take<float>((size_t)B * D.Pq * D.d);
   ws->gq = a.take<float>((size_t)B * D.L);
-  ws->w1t = a.take<float>((size_t)D.L * D.H);
-  ws->w2t = a.take<float>((size_t)D.L * D.H);
+  {
+    Prepared measure;
+    plan_prepared(s, nullptr, 0, &measure);
+    char* blob = a.take<char>(measure.total);
+    plan_prepared(s, blob, blob ? measure.total : 0, &ws->prep);
+  }
   ws->stage_q = a.take<float>((size_t)B * D.Dq);
   ws->stage_uid = a.take<int64_t>((size_t)B);
   ws->stage_out_scores = a.take<float>((size_t)B * k);
@@ -184,7 +245,13 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
     int64_t sample = 32 * N / target;  // -> threshold rank m >= 32 in the sample
     if (sample < 32768) sample = 32768;
     sample = (sample + 127) / 128 * 128;
+    // the sample is every stride-th item tile, so that an ordered corpus (by popularity, id, cluster, ...) still gives
+    // a representative threshold; the main pass scores the complement
+    const int64_t tiles = (N + 127) / 128;
+    int64_t stride = tiles / (sample / 128);
+    if (stride < 2) stride = 1;  // (cannot happen with cap * 16 <= N; kept as the contiguous fallback)
     ws->sample = sample;
+    ws->samp_stride = (int)stride;
     ws->m = (int)((target * sample + N - 1) / N);
     ws->chunk = B < 1 ? 1 : B;
     int64_t fb = (int64_t)(1ull << 30) / (int64_t)(sizeof(float) * (size_t)n_rows);
@@ -208,6 +275,8 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
     ws->fcnt = a.take<int32_t>((size_t)ws->chunk);
     ws->fscores = a.take<float>((size_t)ws->chunk * ws->cap);
     ws->fidx = a.take<int32_t>((size_t)ws->chunk * ws->cap);
+    ws->map_sample = a.take<int32_t>((size_t)(sample / 128));
+    ws->map_main = a.take<int32_t>((size_t)tiles);
   } else {
     // query chunk so that the (chunk, N) score matrix stays <= 4 GiB
     int64_t max_rows = (int64_t)(4ull << 30) / (int64_t)(sizeof(float) * (size_t)n_rows);
@@ -217,6 +286,7 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
     ws->chunk = chunk;
     ws->chunk_fb = chunk;
     ws->sample = 0;
+    ws->samp_stride = 1;
     ws->m = 0;
     ws->S = 0;
     ws->scores = a.take<float>((size_t)chunk * (size_t)N);
@@ -227,6 +297,7 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
     ws->fcnt = nullptr;
     ws->fscores = nullptr;
     ws->fidx = nullptr;
+    ws->map_sample = ws->map_main = nullptr;
   }
   ws->cand_scores = a.take<float>((size_t)ws->chunk * ws->Kp);
   ws->cand_idx = a.take<int32_t>((size_t)ws->chunk * ws->Kp);
@@ -234,6 +305,8 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
   ws->flags = a.take<int32_t>((size_t)ws->chunk);
   memset(&ws->coarse, 0, sizeof(ws->coarse));
   if (tensor) coarse_plan(s, ws->chunk, a, &ws->coarse);
+  ws->coarse.w1_img = ws->prep.w1_img;
+  ws->coarse.w2_img = ws->prep.w2_img;
   ws->total = align_up(a.off, 256);
   if (base != nullptr && a.off > cap) {
     set_error("workspace too small: need %zu bytes, got %zu", ws->total, cap);
@@ -280,14 +353,14 @@ static int topk_of_matrix(const SearchWs& ws, const float* scores, int64_t n, in
 // Flagged queries are re-done exactly, in sub-chunks whose (rows, N) fp32 matrix fits the workspace (kernels
 // exit immediately for unflagged rows).
 static int exact_fallback(const mol_shape_t& s, const mol_weights_t& w, const mol_index_t& ix, const SearchWs& ws,
-                          const float* qsub, const float* gq, int bc, int k, float* o_scores, int64_t* o_ids,
-                          cudaStream_t st) {
+                          const Prepared& prep, const float* qsub, const float* gq, int bc, int k, float* o_scores,
+                          int64_t* o_ids, cudaStream_t st) {
   Dims D = dims_of(s);
   const int64_t N = ix.num_items;
   for (int b1 = 0; b1 < bc; b1 += ws.chunk_fb) {
     const int nb = (bc - b1 < ws.chunk_fb) ? (bc - b1) : ws.chunk_fb;
     const int32_t* fl = ws.flags + b1;
-    MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub + (size_t)b1 * D.Pq * D.d, gq + (size_t)b1 * D.L, nb,
+    MOL_TRY(launch_exact_scores(s, w, ix, prep.w1t, prep.w2t, qsub + (size_t)b1 * D.Pq * D.d, gq + (size_t)b1 * D.L, nb,
                                 nullptr, N, N, ws.scores, fl, st));
     MOL_TRY(topk_of_matrix(ws, ws.scores, N, N, nb, k, o_scores + (size_t)b1 * k, nullptr, o_ids + (size_t)b1 * k,
                            ix.item_ids, fl, st));
@@ -295,17 +368,36 @@ static int exact_fallback(const mol_shape_t& s, const mol_weights_t& w, const mo
   return MOL_OK;
 }
 
+__global__ void stats_init_kernel(int32_t* stats, int filter, int tensor, int kp, int cap) {
+  if (threadIdx.x < kNumStats) stats[threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    stats[3] = filter;
+    stats[4] = tensor;
+    stats[6] = kp;
+    stats[7] = cap;
+  }
+}
+
 static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_index_t& ix,
                        const float* queries, const int64_t* user_ids, int B, int k, int mode,
-                       float* out_scores, int64_t* out_ids, const SearchWs& ws, cudaStream_t st) {
+                       float* out_scores, int64_t* out_ids, const SearchWs& ws_in, cudaStream_t st) {
   Dims D = dims_of(s);
   const int64_t N = ix.num_items;
   const bool tensor = use_tensor(s, mode);
-  MOL_TRY(run_query_prologue(s, w, queries, user_ids, B, ws.pre, ws.h, ws.proj, ws.hq, ws.qsub,
-                             ws.gq, st));
-  MOL_TRY(launch_transpose(w.qi_w1, ws.w1t, D.H, D.L, st));  // (H,L) -> (L,H)
-  MOL_TRY(launch_transpose(w.qi_w2, ws.w2t, D.L, D.H, st));  // (L,H) -> (H,L)
-  if (tensor) MOL_TRY(coarse_prepare(s, w, ws.coarse, st));
+  SearchWs ws = ws_in;
+  Prepared prep;
+  {
+    NvtxRange r("mol:prologue");
+    stats_init_kernel<<<1, 32, 0, st>>>(ws.stats, ws.filter, tensor ? 1 : 0, ws.Kp, ws.cap);
+    MOL_LAUNCH_CHECK();
+    MOL_TRY(run_query_prologue(s, w, queries, user_ids, B, ws.pre, ws.h, ws.proj, ws.hq, ws.qsub, ws.gq, st));
+    MOL_TRY(get_prepared(s, w, ws.prep, &prep, st));
+    ws.coarse.w1_img = prep.w1_img;
+    ws.coarse.w2_img = prep.w2_img;
+    if (tensor && ws.filter && ws.samp_stride > 1)
+      MOL_TRY(coarse_tile_maps(ws.map_sample, ws.map_main, (int)((N + 127) / 128), ws.samp_stride, (int)(ws.sample / 128), st));
+  }
 
   for (int b0 = 0; b0 < B; b0 += ws.chunk) {
     const int bc = (B - b0 < ws.chunk) ? (B - b0) : ws.chunk;
@@ -314,64 +406,88 @@ static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_i
     float* o_scores = out_scores + (size_t)b0 * k;
     int64_t* o_ids = out_ids + (size_t)b0 * k;
     if (!tensor) {
+      NvtxRange r("mol:exact");
       prof_begin(st);
-      MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub, gq, bc, nullptr, N, N, ws.scores, nullptr, st));
+      MOL_TRY(launch_exact_scores(s, w, ix, prep.w1t, prep.w2t, qsub, gq, bc, nullptr, N, N, ws.scores, nullptr, st));
       prof_end(st);
       MOL_TRY(topk_of_matrix(ws, ws.scores, N, N, bc, k, o_scores, nullptr, o_ids, ix.item_ids, nullptr, st));
       continue;
     }
     const int kk = ws.Kp;
     const float* thr = nullptr;
+    MOL_TRY(coarse_query_records(s, ws.coarse, qsub, gq, bc, prep.overflow, st));
     if (!ws.filter) {
       // matrix strategy: coarse scores of every pair -> top-K' per query
-      prof_begin(st);
-      MOL_TRY(coarse_scores(s, ix, ws.coarse, qsub, gq, bc, ws.scores, st));
-      prof_end(st);
+      {
+        NvtxRange r("mol:coarse");
+        prof_begin(st);
+        MOL_TRY(coarse_scores(s, ix, ws.coarse, bc, ws.scores, st));
+        prof_end(st);
+      }
+      NvtxRange r("mol:select");
       MOL_TRY(topk_of_matrix(ws, ws.scores, N, N, bc, kk, ws.cand_scores, ws.cand_idx, nullptr, nullptr, nullptr, st));
     } else {
-      // filter strategy.  (1) threshold pass over the first `sample` items
+      // filter strategy.  (1) threshold pass over a strided sample of the item tiles
       const int sample_tiles = (int)(ws.sample / 128);
-      CoarseOut o1{};
-      o1.scores = ws.scores;
-      o1.ld = ws.sample;
-      o1.tile_begin = 0;
-      o1.tile_end = sample_tiles;
-      prof_begin(st);
-      MOL_TRY(coarse_run(s, ix, ws.coarse, qsub, gq, bc, o1, st));
-      prof_end(st);
-      MOL_TRY(topk_of_matrix(ws, ws.scores, ws.sample, ws.sample, bc, ws.m, ws.samp_top, nullptr, nullptr, nullptr,
-                             nullptr, st));
-      thr = ws.samp_top + (ws.m - 1);  // stride m
-      // (2) survivors of the sample, then the main pass with the filter fused into the scoring kernel
-      MOL_CUDA(cudaMemsetAsync(ws.fcnt, 0, (size_t)bc * sizeof(int32_t), st));
-      MOL_CUDA(cudaMemsetAsync(ws.fidx, 0xFF, (size_t)bc * ws.cap * sizeof(int32_t), st));
-      MOL_TRY(coarse_filter_matrix(ws.scores, ws.sample, ws.sample, bc, thr, ws.m, ws.fcnt, ws.fscores, ws.fidx,
-                                   ws.cap, st));
-      CoarseOut o2{};
-      o2.thr = thr;
-      o2.thr_stride = ws.m;
-      o2.cand_cnt = ws.fcnt;
-      o2.cand_scores = ws.fscores;
-      o2.cand_idx = ws.fidx;
-      o2.cand_cap = ws.cap;
-      o2.tile_begin = sample_tiles;
-      o2.tile_end = -1;
-      prof_begin(st);
-      MOL_TRY(coarse_run(s, ix, ws.coarse, qsub, gq, bc, o2, st));
-      prof_end(st);
+      {
+        NvtxRange r("mol:coarse_sample");
+        CoarseOut o1{};
+        o1.scores = ws.scores;
+        o1.ld = ws.sample;
+        o1.tile_begin = 0;
+        o1.tile_end = sample_tiles;
+        o1.tile_map = ws.samp_stride > 1 ? ws.map_sample : nullptr;
+        prof_begin(st);
+        MOL_TRY(coarse_run(s, ix, ws.coarse, bc, o1, st));
+        prof_end(st);
+        MOL_TRY(topk_of_matrix(ws, ws.scores, ws.sample, ws.sample, bc, ws.m, ws.samp_top, nullptr, nullptr, nullptr,
+                               nullptr, st));
+        thr = ws.samp_top + (ws.m - 1);  // stride m
+        // (2) survivors of the sample
+        MOL_CUDA(cudaMemsetAsync(ws.fcnt, 0, (size_t)bc * sizeof(int32_t), st));
+        MOL_CUDA(cudaMemsetAsync(ws.fidx, 0xFF, (size_t)bc * ws.cap * sizeof(int32_t), st));
+        MOL_TRY(coarse_filter_matrix(ws.scores, ws.sample, ws.sample, bc, thr, ws.m, ws.fcnt, ws.fscores, ws.fidx,
+                                     ws.cap, ws.samp_stride, st));
+      }
+      {
+        // ... then the main pass over every other tile, the filter fused into the scoring kernel's epilogue
+        NvtxRange r("mol:coarse_main");
+        CoarseOut o2{};
+        o2.thr = thr;
+        o2.thr_stride = ws.m;
+        o2.cand_cnt = ws.fcnt;
+        o2.cand_scores = ws.fscores;
+        o2.cand_idx = ws.fidx;
+        o2.cand_cap = ws.cap;
+        const int tiles = (int)((N + 127) / 128);
+        if (ws.samp_stride > 1) {
+          o2.tile_map = ws.map_main;
+          o2.tile_begin = 0;
+          o2.tile_end = tiles - sample_tiles;
+        } else {
+          o2.tile_begin = sample_tiles;
+          o2.tile_end = tiles;
+        }
+        prof_begin(st);
+        MOL_TRY(coarse_run(s, ix, ws.coarse, bc, o2, st));
+        prof_end(st);
+      }
       // (3) the K' best survivors per query
+      NvtxRange r("mol:select");
       MOL_TRY(launch_select_final_i32(ws.fscores, ws.fidx, ws.cap, ws.cap, bc, kk, ws.cand_scores, ws.cand_idx,
                                       nullptr, nullptr, nullptr, st));
     }
     // exact fp32 rescoring of the K' candidates -> final top-k (+ safety check and per-query exact fallback)
-    MOL_TRY(launch_exact_scores(s, w, ix, ws.w1t, ws.w2t, qsub, gq, bc, ws.cand_idx, kk, kk, ws.exact_scores,
+    NvtxRange r("mol:rescore");
+    MOL_TRY(launch_exact_scores(s, w, ix, prep.w1t, prep.w2t, qsub, gq, bc, ws.cand_idx, kk, kk, ws.exact_scores,
                                 nullptr, st));
     MOL_TRY(launch_select_final_i32(ws.exact_scores, ws.cand_idx, kk, kk, bc, k, o_scores, nullptr, o_ids,
                                     ix.item_ids, nullptr, st));
     if (kk < N) {
       MOL_TRY(coarse_safety_flags(ws.cand_scores, ws.exact_scores, o_scores, bc, kk, k, ws.coarse.overflow,
-                                  ix.half_overflow, ws.filter ? ws.fcnt : nullptr, thr, ws.m, ws.cap, ws.flags, st));
-      MOL_TRY(exact_fallback(s, w, ix, ws, qsub, gq, bc, k, o_scores, o_ids, st));
+                                  ix.half_overflow, ws.filter ? ws.fcnt : nullptr, thr, ws.m, ws.cap, ws.flags,
+                                  ws.stats, st));
+      MOL_TRY(exact_fallback(s, w, ix, ws, prep, qsub, gq, bc, k, o_scores, o_ids, st));
     }
   }
   return MOL_OK;
@@ -418,6 +534,34 @@ int mol_profile_collect(double* total_ms, int32_t* launches) {
 int mol_shape_check(const mol_shape_t* shape, int32_t* tensor_ok) {
   MOL_TRY(check_shape(shape));
   if (tensor_ok) *tensor_ok = coarse_supported(*shape) ? 1 : 0;
+  return MOL_OK;
+}
+
+int mol_weights_prepared_bytes(const mol_shape_t* shape, size_t* bytes) {
+  MOL_TRY(check_shape(shape));
+  MOL_CHECK_ARG(bytes, "bytes is NULL");
+  Prepared p;
+  plan_prepared(*shape, nullptr, 0, &p);
+  *bytes = p.total;
+  return MOL_OK;
+}
+
+int mol_weights_prepare(const mol_shape_t* shape, const mol_weights_t* w, void* blob, size_t blob_bytes,
+                        mol_stream_t stream) {
+  MOL_TRY(check_shape(shape));
+  MOL_TRY(check_weights(shape, w));
+  MOL_CHECK_ARG(blob && (reinterpret_cast<uintptr_t>(blob) & 255) == 0, "prepared blob must be 256-byte aligned");
+  Prepared p;
+  plan_prepared(*shape, blob, blob_bytes, &p);
+  MOL_CHECK_ARG(p.total <= blob_bytes, "prepared blob too small: need %zu, got %zu", p.total, blob_bytes);
+  return run_prepare(*shape, *w, p, static_cast<cudaStream_t>(stream));
+}
+
+int mol_search_stats(const void* workspace, int32_t* host_stats, mol_stream_t stream) {
+  MOL_CHECK_ARG(workspace && host_stats, "NULL buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MOL_CUDA(cudaMemcpyAsync(host_stats, workspace, kNumStats * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MOL_CUDA(cudaStreamSynchronize(st));
   return MOL_OK;
 }
 
@@ -583,9 +727,9 @@ int mol_score_all(const mol_shape_t* shape, const mol_weights_t* w, const mol_in
   Dims D = dims_of(*shape);
   MOL_TRY(run_query_prologue(*shape, *w, queries, user_ids, B, ws.pre, ws.h, ws.proj, ws.hq, ws.qsub,
                              ws.gq, st));
-  MOL_TRY(launch_transpose(w->qi_w1, ws.w1t, D.H, D.L, st));
-  MOL_TRY(launch_transpose(w->qi_w2, ws.w2t, D.L, D.H, st));
-  return launch_exact_scores(*shape, *w, *index, ws.w1t, ws.w2t, ws.qsub, ws.gq, B, nullptr,
+  Prepared prep;
+  MOL_TRY(get_prepared(*shape, *w, ws.prep, &prep, st));
+  return launch_exact_scores(*shape, *w, *index, prep.w1t, prep.w2t, ws.qsub, ws.gq, B, nullptr,
                              index->num_items, index->num_items, out_scores, nullptr, st);
 }
 
@@ -605,8 +749,12 @@ int mol_score_all_coarse(const mol_shape_t* shape, const mol_weights_t* w, const
   MOL_TRY(plan_search(*shape, /*N=*/1, B, 1, MOL_MODE_TENSOR, workspace, workspace_bytes, &ws));
   MOL_TRY(run_query_prologue(*shape, *w, queries, user_ids, B, ws.pre, ws.h, ws.proj, ws.hq, ws.qsub,
                              ws.gq, st));
-  MOL_TRY(coarse_prepare(*shape, *w, ws.coarse, st));
-  return coarse_scores(*shape, *index, ws.coarse, ws.qsub, ws.gq, B, out_scores, st);
+  Prepared prep;
+  MOL_TRY(get_prepared(*shape, *w, ws.prep, &prep, st));
+  ws.coarse.w1_img = prep.w1_img;
+  ws.coarse.w2_img = prep.w2_img;
+  MOL_TRY(coarse_query_records(*shape, ws.coarse, ws.qsub, ws.gq, B, prep.overflow, st));
+  return coarse_scores(*shape, *index, ws.coarse, B, out_scores, st);
 }
 
 }  // extern "C"
@@ -1033,6 +1181,100 @@ int mol_merge_topk(const float* part_scores, const int64_t* part_ids, int32_t R,
   merge_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part_scores, part_ids, gs, gi, R, B, k);
   MOL_LAUNCH_CHECK();
   return launch_select_final_i64(gs, gi, (int64_t)R * k, (int64_t)R * k, B, k, out_scores, out_ids, st);
+}
+
+}  // extern "C"
+
+namespace mol {
+// ---- packed partial top-k lists: the payload of the single all-gather of the multi-GPU paths -------------------------
+struct __align__(16) PackedEntry {
+  int64_t id;
+  float score;
+  int32_t valid;
+};
+static_assert(sizeof(PackedEntry) == MOL_PACKED_ENTRY_BYTES, "packed entry layout");
+
+__global__ void pack_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int B, int k_valid,
+                                 int k, PackedEntry* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * k) return;
+  const int b = (int)(i / k), j = (int)(i % k);
+  PackedEntry e;
+  if (j < k_valid) {
+    e.id = ids[(int64_t)b * k_valid + j];
+    e.score = scores[(int64_t)b * k_valid + j];
+    e.valid = 1;
+  } else {
+    e.id = -1;
+    e.score = -__int_as_float(0x7f800000);
+    e.valid = 0;
+  }
+  out[i] = e;
+}
+
+// gathered (R, B, k) entries -> per query row (B, R*k): scores, payload = flat position in the row-major (B, R*k) id
+// array (or -1 for a padding entry), ids
+__global__ void unpack_gathered_kernel(const PackedEntry* __restrict__ g, int R, int B, int k, float* __restrict__ os,
+                                       int32_t* __restrict__ op, int64_t* __restrict__ oi) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)R * B * k;
+  if (i >= total) return;
+  const int r = (int)(i / ((int64_t)B * k));
+  const int64_t rem = i % ((int64_t)B * k);
+  const int b = (int)(rem / k), j = (int)(rem % k);
+  const int64_t o = ((int64_t)b * R + r) * k + j;
+  const PackedEntry e = g[i];
+  os[o] = e.valid ? e.score : -__int_as_float(0x7f800000);
+  op[o] = e.valid ? (int32_t)o : -1;
+  oi[o] = e.id;
+}
+}  // namespace mol
+
+extern "C" {
+
+int mol_pack_topk(const float* scores, const int64_t* ids, int32_t B, int32_t k_valid, int32_t k, void* out_packed,
+                  mol_stream_t stream) {
+  MOL_CHECK_ARG(B >= 0 && k >= 1 && k_valid >= 0 && k_valid <= k, "bad arguments");
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(out_packed && (k_valid == 0 || (scores && ids)), "NULL buffer");
+  const int64_t total = (int64_t)B * k;
+  pack_topk_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, ids, B, k_valid, k, static_cast<PackedEntry*>(out_packed));
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
+int mol_merge_topk_packed_workspace_bytes(int32_t R, int32_t B, int32_t k, size_t* bytes) {
+  MOL_CHECK_ARG(bytes && R >= 1 && B >= 0 && k >= 1, "bad arguments");
+  const size_t n = (size_t)R * B * k;
+  *bytes = align_up(n * sizeof(float), 256) + align_up(n * sizeof(int32_t), 256) + align_up(n * sizeof(int64_t), 256) + 512;
+  return MOL_OK;
+}
+
+int mol_merge_topk_packed(const void* gathered, int32_t R, int32_t B, int32_t k, float* out_scores, int64_t* out_ids,
+                          void* workspace, size_t workspace_bytes, mol_stream_t stream) {
+  MOL_CHECK_ARG(R >= 1 && B >= 0 && k >= 1 && k <= MOL_MAX_K, "bad arguments");
+  MOL_CHECK_ARG((int64_t)R * B * k < (1ll << 31), "R * B * k must fit int32");
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(gathered && out_scores && out_ids, "NULL buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t need;
+  MOL_TRY(mol_merge_topk_packed_workspace_bytes(R, B, k, &need));
+  if (!workspace || workspace_bytes < need) {
+    set_error("merge workspace too small: need %zu, got %zu", need, workspace_bytes);
+    return MOL_ERR_WORKSPACE;
+  }
+  Arena a(workspace, workspace_bytes);
+  const int64_t total = (int64_t)R * B * k;
+  float* gs = a.take<float>((size_t)total);
+  int32_t* gp = a.take<int32_t>((size_t)total);
+  int64_t* gi = a.take<int64_t>((size_t)total);
+  unpack_gathered_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(static_cast<const PackedEntry*>(gathered), R, B,
+                                                                          k, gs, gp, gi);
+  MOL_LAUNCH_CHECK();
+  // padding entries carry payload -1 (ignored by the select); ties: lower rank, then lower position, first
+  return launch_select_final_i32(gs, gp, (int64_t)R * k, (int64_t)R * k, B, k, out_scores, nullptr, out_ids, gi, nullptr,
+                                 st);
 }
 
 }  // extern "C"

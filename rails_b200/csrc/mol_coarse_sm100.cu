@@ -52,7 +52,10 @@ constexpr int kThreads = kEpiThreads + 4 * 32;
 #ifndef MOL_E2_REGS
 #define MOL_E2_REGS 56
 #endif
-constexpr int kE2Regs = MOL_E2_REGS, kE13Regs = 216 - kE2Regs, kCtlRegs = 48;
+#ifndef MOL_CTL_REGS
+#define MOL_CTL_REGS 80  // measured (round 2): 48 made ptxas spill the issuer loops (LDL in front of tcgen05.mma): 35.4 -> 33.2 ms per step
+#endif
+constexpr int kE2Regs = MOL_E2_REGS, kCtlRegs = MOL_CTL_REGS, kE13Regs = 240 - kE2Regs - kCtlRegs / 2;
 static_assert(256 * kE13Regs + 256 * kE2Regs + 128 * kCtlRegs <= kThreads * 96, "register pool over-committed");
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kK3 = kH + 16;    // K of the gate GEMM's TS part: hidden units + the ones block
@@ -85,7 +88,7 @@ constexpr bool kG1Pair = MOL_G1_PAIR != 0;
 static_assert(!(kG1Pair && kG1Split), "MOL_G1_PAIR and MOL_G1_SPLIT are exclusive");
 static_assert(!(kG1Late && (kG1Split || kG1Pair)), "MOL_G1_LATE excludes MOL_G1_SPLIT / MOL_G1_PAIR");
 #ifndef MOL_E2_POLY_MASK
-#define MOL_E2_POLY_MASK 0x0E
+#define MOL_E2_POLY_MASK 0  // (round 1 shipped 0x0E; the half2 form below measured 5.5 % faster)
 #endif
 // bit c set: chunk c (16 hidden units) of E2 takes tanh from an fp32 odd polynomial on the FMA pipe instead of MUFU.TANH
 constexpr unsigned kE2PolyMask = MOL_E2_POLY_MASK;
@@ -129,7 +132,7 @@ constexpr float kT0 = 0.996860146522522f, kT1 = -0.3149697482585907f, kT2 = 0.10
 // max |error of h| 2.7e-3, rms 3.5e-4 over every fp16 u in [-12, 12] - the MUFU.TANH.F16 path has 2.9e-3 / 2.7e-4 before the
 // MUFU's own error.  10 half2 instructions per pair of values after the f32 -> f16x2 pack, none of them on the MUFU.
 #ifndef MOL_E2_H2_MASK
-#define MOL_E2_H2_MASK 0
+#define MOL_E2_H2_MASK 0x3E  // measured (round 2, B200): 33.3 ms vs 35.3 ms per 512 x 1M step, final ids / scores identical
 #endif
 // bit c set: chunk c (16 hidden units) of E2 uses the half2 form (takes precedence over MOL_E2_POLY_MASK for that chunk)
 constexpr unsigned kE2H2Mask = MOL_E2_H2_MASK;
@@ -211,7 +214,7 @@ struct CoarseCfg {
   static constexpr int QV = Q_BYTES / 16 / 128;  // uint4 per epilogue thread when staging a query image
   static constexpr int D_BYTES = L * L * 2;      // diag(0.5 gq) image
   static constexpr int QREC_BYTES = Q_BYTES + L * 2;  // per-query record in global memory: image | 0.5 gq (fp16, l' order)
-  static constexpr int FIXED = W1_BYTES + W2_BYTES + 2 * Q_BYTES + 2 * D_BYTES + 4096 /*ones tile (X-resident variant)*/ + 512 /*barriers*/ + 1024 /*alignment*/;
+  static constexpr int FIXED = W1_BYTES + W2_BYTES + 2 * Q_BYTES + 2 * D_BYTES + 512 /*barriers*/ + 1024 /*alignment*/;
   static constexpr int STAGES = (2 * (X_BYTES + GI_BYTES) + FIXED <= kSmemLimit) ? 2 : 1;
   static constexpr int SMEM_BYTES = STAGES * (X_BYTES + GI_BYTES) + FIXED;
   static_assert(SMEM_BYTES <= kSmemLimit, "shared memory budget exceeded");
@@ -244,8 +247,10 @@ struct CoarseParams {
   int cand_cap;
   int64_t N;
   int64_t ld;             // row stride of `scores`
-  int tile_begin, tile_end;  // item tiles [tile_begin, tile_end) are scored; scores column = item - tile_begin * 128
+  int tile_begin, tile_end;  // LOGICAL item tiles [tile_begin, tile_end) are scored; scores column = (tile - tile_begin) * 128 + row
+  const int32_t* tile_map;   // physical item tile of each logical tile (CoarseOut::tile_map), or nullptr = identity
   int bc;
+  __device__ __forceinline__ int phys_tile(int i) const { return tile_map ? __ldg(tile_map + i) : i; }
 };
 
 // canonical no-swizzle K-major UMMA layout of an R x K 16-bit matrix (8x8 core matrices, K-adjacent cores contiguous)
@@ -420,10 +425,11 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
         mbar_wait_sleep(&bars->empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&bars->full[s], C::X_BYTES + C::GI_BYTES);
+        const int pt = P.phys_tile(t0 + w.tile);
 #pragma unroll
         for (int bx = 0; bx < C::XBOXES; ++bx)
-          tma_load_2d(sX + s * C::X_BYTES + bx * 16384, &tmX, &bars->full[s], bx * 64, (t0 + w.tile) * kTile);
-        tma_load_2d(sGI + s * C::GI_BYTES, &tmGI, &bars->full[s], 0, (t0 + w.tile) * kTile);
+          tma_load_2d(sX + s * C::X_BYTES + bx * 16384, &tmX, &bars->full[s], bx * 64, pt * kTile);
+        tma_load_2d(sGI + s * C::GI_BYTES, &tmGI, &bars->full[s], 0, pt * kTile);
         ++it;
       }
     }
@@ -825,6 +831,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (warp == 0) TR(0, 2, cnt);
     };
 
+    int map_tile = -1, map_phys = 0;
     // E3 of query (tile_p, q_p) (gate_full phase `par`).  Once GATE is in registers it stages the diag of the next
     // query in sequence (if any: its G3 is the next writer of GATE and the next reader of the diag) and releases both.
     auto e3 = [&](const uint32_t (&pk)[L / 2], int tile_p, int q_p, uint32_t par, bool stage_diag) __attribute__((always_inline)) {
@@ -933,7 +940,11 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const float2 d2 = __fadd2_rn(__fadd2_rn(den[0], den[1]), __fadd2_rn(den[2], den[3]));
       const float score = __fdividef(n2.x + n2.y, d2.x + d2.y);
       if (warp == 0) TR(0, 5, cnt - 1u);
-      const int64_t item = (int64_t)(t0 + tile_p) * kTile + r;
+      if (tile_p != map_tile) {  // (the logical -> physical map has integer divisions: once per tile, not per query)
+        map_tile = tile_p;
+        map_phys = P.phys_tile(t0 + tile_p);
+      }
+      const int64_t item = (int64_t)map_phys * kTile + r;
       if (item < P.N) {
         if (P.scores) P.scores[(size_t)q_p * P.ld + ((int64_t)tile_p * kTile + r)] = score;
         if (P.thr && !(score < thr_q)) {  // NaN passes the filter on purpose
@@ -1017,565 +1028,6 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == kCtlWarp0) tmem_dealloc<512>(tmem);
 }
 
-#ifdef MOL_COARSE_XRES
-// ================================================================================================
-// X-resident variant (mol_coarse_xres_kernel; build with -DMOL_COARSE_XRES): the item tile lives in TENSOR MEMORY.
-// Parity-green (same tests) but measured SLOWER than the two-slot kernel above on B200 (47 ms vs 39 ms per
-// 512 x 1M step): with a single HID accumulator the G2 -> E2 chain of consecutive queries serialises, and the two-slot
-// kernel's second slot hides exactly that latency.  Kept as the measured alternative.
-//
-// Measured on B200 (tools/run_probe.py mma_rate): an SS tcgen05.mma (A from shared memory) costs ~41 clk + N/2 — the
-// 4 KB A fetch — while a TS one (A from TMEM) costs ~9 clk + N/2.  With the item tile as the SS A operand, G1 (16 MMAs
-// of N = 16 per query) spent ~790 clk per (query, tile) on the tensor pipe, 44 % of its occupancy, and the pipe was the
-// co-bottleneck with the MUFU.  Here the tile is copied once per tile from the TMA landing zone into TMEM (fp16,
-// XCOLS / 2 columns) and every G1 is a TS MMA (~270 clk per query).  That takes 128 of the 512 columns, so there is ONE
-// pipeline of queries per SM instead of two slots, and all four epilogue warpgroups work on it:
-//   warps 0-3 / 4-7    E3 group of even / odd queries (own GATE buffer each): gate -> softmax-weighted score -> output
-//   warps 8-11 / 12-15 E1/E2 groups, each owning HALF the columns of every query: logits -> fp16 operand (+ a stash
-//                      copy for E3), hidden pre-activations -> silu -> fp16 operand; they also copy X into TMEM
-//   warp 16 MMA issuer (converged warp, elected lane), warp 18 TMA producer.
-// TMEM columns: XT [0, XCOLS/2) | LOG L (A2 aliases it) | HID 128 (A3 aliases it) | GATE0 L | GATE1 L | STASH0 L/2 |
-// STASH1 L/2  (= 512 for 8x8x32 and 8x4x128).
-// ================================================================================================
-template <int PX, int DD>
-struct XresCfg {
-  using C = CoarseCfg<PX, DD>;
-  static constexpr int L = C::L;
-  static constexpr int LH = L / 2;                       // fp32 LOG / GATE columns per E1/E2 group
-  static constexpr uint32_t XT = 0;
-  static constexpr uint32_t LOG = C::XCOLS / 2;
-  static constexpr uint32_t HID = LOG + L;
-  static constexpr uint32_t GATE0 = HID + kH;
-  static constexpr uint32_t STASH0 = GATE0 + 2 * L;
-  static constexpr uint32_t END = STASH0 + L;
-  static_assert(END <= 512, "TMEM budget exceeded");
-  static constexpr int XB_HALF = C::XBOXES / 2;          // 64-column boxes of the X row copied by each E1/E2 group
-  static_assert(C::XBOXES % 2 == 0, "X row must split into two halves of whole boxes");
-};
-
-struct XBars {
-  uint64_t full[2], empty[2];
-  uint64_t xt_ready, q0_ready, log_full, log_free, hid_full, e2a_done, e2b_done;
-  uint64_t gate_full[2], gate_free[2], stash_ready[2], stash_free[2];
-  uint32_t tmem_base;
-};
-
-constexpr int kXA_Regs = 136, kXB_Regs = 80, kXC_Regs = 48;
-static_assert(256 * kXA_Regs + 256 * kXB_Regs + 128 * kXC_Regs <= kThreads * 96, "register pool over-committed");
-
-// flat sequence of this CTA's (tile, query) units; `c` counts them
-struct FlatSeq {
-  TileWalk w;
-  int q;
-  bool in_tile;
-  int it;  // index of the current tile within this CTA's walk
-  __device__ FlatSeq(int64_t f0, int64_t f1, int bc) : w(f0, f1, bc), q(0), in_tile(false), it(-1) {}
-  // advances by one unit; first = first query of a tile for this CTA
-  __device__ bool next(int& tile, int& query, bool& first) {
-    first = false;
-    if (!(in_tile && q < w.qb)) {
-      if (!w.next()) return false;
-      q = w.qa;
-      in_tile = true;
-      first = true;
-      ++it;
-    }
-    tile = w.tile;
-    query = q++;
-    return true;
-  }
-};
-
-template <int PX, int DD>
-__global__ void __launch_bounds__(kThreads, 1)
-mol_coarse_xres_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmGI,
-                       const CoarseParams P) {
-  using C = CoarseCfg<PX, DD>;
-  using X = XresCfg<PX, DD>;
-  constexpr int L = C::L, LH = X::LH;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* sX = smem;                                   // STAGES x X_BYTES   (TMA landing zone)
-  unsigned char* sGI = sX + C::STAGES * C::X_BYTES;           // STAGES x GI_BYTES  (SS operand of G3 for the whole tile)
-  unsigned char* sW1 = sGI + C::STAGES * C::GI_BYTES;
-  unsigned char* sW2 = sW1 + C::W1_BYTES;
-  unsigned char* sQ = sW2 + C::W2_BYTES;                      // 2 x Q_BYTES, by query parity
-  unsigned char* sD = sQ + 2 * C::Q_BYTES;                    // 2 x D_BYTES, by query parity
-  unsigned char* sOnes = sD + 2 * C::D_BYTES;                 // 128 x 16 fp16, column 0 = 1: SS A operand that adds the biases
-  XBars* bars = reinterpret_cast<XBars*>(sOnes + 4096);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  for (int i = tid; i < C::W1_BYTES / 16; i += kThreads)
-    reinterpret_cast<uint4*>(sW1)[i] = reinterpret_cast<const uint4*>(P.w1_img)[i];
-  for (int i = tid; i < C::W2_BYTES / 16; i += kThreads)
-    reinterpret_cast<uint4*>(sW2)[i] = reinterpret_cast<const uint4*>(P.w2_img)[i];
-  for (int i = tid; i < 2 * C::D_BYTES / 16; i += kThreads) reinterpret_cast<uint4*>(sD)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 4096 / 16; i += kThreads)  // row r of the ones tile: 16 bytes at (r >> 3) * 256 + (r & 7) * 16
-    reinterpret_cast<uint4*>(sOnes)[i] = ((i >> 3) & 1) ? make_uint4(0, 0, 0, 0) : make_uint4(0x00003C00u, 0, 0, 0);
-  if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], 1);
-      mbar_init(&bars->gate_full[s], 1);
-      mbar_init(&bars->gate_free[s], 128);
-      mbar_init(&bars->stash_ready[s], 256);
-      mbar_init(&bars->stash_free[s], 128);
-    }
-    mbar_init(&bars->xt_ready, 256);
-    mbar_init(&bars->q0_ready, 128);
-    mbar_init(&bars->log_full, 1);
-    mbar_init(&bars->log_free, 256);
-    mbar_init(&bars->hid_full, 1);
-    mbar_init(&bars->e2a_done, 128);
-    mbar_init(&bars->e2b_done, 128);
-    fence_mbar_init();
-  }
-  if (warp == kCtlWarp0) tmem_alloc<512>(&bars->tmem_base);
-  if (warp == kCtlWarp0 + 2 && lane == 0) {
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmGI);
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
-
-  const int64_t F = (int64_t)(P.tile_end - P.tile_begin) * P.bc;
-  const int64_t f0 = F * blockIdx.x / gridDim.x, f1 = F * (blockIdx.x + 1) / gridDim.x;
-  const int t0 = P.tile_begin;
-
-  if (warp >= kCtlWarp0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kXC_Regs));
-  if (warp == kCtlWarp0 + 2) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
-      TileWalk w(f0, f1, P.bc);
-      int it = 0;
-      while (w.next()) {
-        const int s = it % C::STAGES;
-        const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-        mbar_wait_sleep(&bars->empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&bars->full[s], C::X_BYTES + C::GI_BYTES);
-#pragma unroll
-        for (int bx = 0; bx < C::XBOXES; ++bx)
-          tma_load_2d(sX + s * C::X_BYTES + bx * 16384, &tmX, &bars->full[s], bx * 64, (t0 + w.tile) * kTile);
-        tma_load_2d(sGI + s * C::GI_BYTES, &tmGI, &bars->full[s], 0, (t0 + w.tile) * kTile);
-        ++it;
-      }
-    }
-  } else if (warp == kCtlWarp0) {
-    // =============================== MMA issuer (converged warp) ===============================
-    constexpr uint32_t idesc1 = make_idesc_f16(128, 16);
-    constexpr uint32_t idesc2 = make_idesc_f16(128, kH);
-    constexpr uint32_t idesc3 = make_idesc_f16(128, L);
-    const uint32_t sW1a = smem_u32(sW1), sW2a = smem_u32(sW2), sQa = smem_u32(sQ), sDa = smem_u32(sD);
-    uint32_t c = 0;  // queries issued so far
-    auto issue_g1 = [&](uint32_t cq) __attribute__((always_inline)) {
-      const uint32_t sQp = sQa + (cq & 1u) * C::Q_BYTES;
-      if (elect_one_sync()) {
-#pragma unroll
-        for (int g = 0; g < C::NG; ++g) {
-#pragma unroll
-          for (int ks = 0; ks < C::K1 / 16; ++ks) {
-            const uint64_t db = make_smem_desc(sQp + ks * 256, 128, (C::K1 / 8) * 128, 0);
-            umma_ts(tmem + X::LOG + g * 16, tmem + X::XT + (g * C::K1 + ks * 16) / 2, db, idesc1, ks > 0);
-          }
-        }
-        umma_commit(&bars->log_full);
-      }
-      __syncwarp();
-    };
-    const uint64_t dOnes = make_smem_desc(smem_u32(sOnes), 128, 256, 0);
-    TileWalk w(f0, f1, P.bc);
-    int it = 0;
-    while (w.next()) {
-      const int s = it % C::STAGES;
-      const int n = w.qb - w.qa;
-      mbar_wait_sleep(&bars->xt_ready, (uint32_t)it & 1u);  // X of this tile is in TMEM (and its GI rows in smem)
-      tc_fence_after();
-      if (c == 0) {
-        mbar_wait_sleep(&bars->q0_ready, 0);
-        tc_fence_after();
-      }
-      // G1 runs two queries ahead of G2: G1(c + 1) as soon as E1 has LOG(c) in registers (log_free), so that the
-      // E1/E2 groups never wait for logits
-      issue_g1(c);
-      if (n > 1) {
-        mbar_wait_sleep(&bars->log_free, c & 1u);
-        tc_fence_after();
-        issue_g1(c + 1);
-      }
-      const uint32_t sGIa = smem_u32(sGI + s * C::GI_BYTES);
-      for (int j = 0; j < n; ++j, ++c) {
-        const uint32_t p = c & 1u, k2 = (c >> 1) & 1u;
-        // ---- G2 once the fp16 logits are in STASH[p] (HID is free: e2a/e2b of the previous query were passed)
-        //      (stash_ready is per query parity: E1 runs one query ahead, a single barrier could be lapped)
-        TR(2, 0, c);
-        mbar_wait_sleep(&bars->stash_ready[p], k2);
-        tc_fence_after();
-        TR(2, 1, c);
-        if (elect_one_sync()) {
-#pragma unroll
-          for (int ks = 0; ks < L / 16; ++ks) {
-            const uint64_t db = make_smem_desc(sW1a + ks * 256, 128, (C::K2 / 8) * 128, 0);
-            umma_ts(tmem + X::HID, tmem + X::STASH0 + p * (L / 2) + ks * 8, db, idesc2, ks > 0);
-          }
-          {  // + 0.5 b1: ones tile (SS) times the bias K-block of the W1 image
-            const uint64_t db = make_smem_desc(sW1a + (L / 16) * 256, 128, (C::K2 / 8) * 128, 0);
-            umma_ss(tmem + X::HID, dOnes, db, idesc2, 1u);
-          }
-          umma_commit(&bars->hid_full);
-        }
-        __syncwarp();
-        if (j + 2 < n) {  // G1(c + 2): LOG(c + 1) is in registers of the E1/E2 groups, image staged during E1(c)
-          mbar_wait_sleep(&bars->log_free, (c + 1u) & 1u);
-          tc_fence_after();
-          issue_g1(c + 2);
-        }
-        TR(2, 2, c);
-        // ---- G3, first part: first half of A3 written, GATE[p] released and diag[p] staged by the E3 group
-        mbar_wait_sleep(&bars->e2a_done, c & 1u);
-        mbar_wait_sleep(&bars->gate_free[p], k2);
-        tc_fence_after();
-        TR(2, 3, c);
-        if (elect_one_sync()) {
-          const uint32_t gate = tmem + X::GATE0 + p * L;
-#pragma unroll
-          for (int ks = 0; ks < L / 16; ++ks) {  // GATE = GI_tile . diag(0.5 gq)
-            const uint64_t da = (L == 64) ? make_smem_desc(sGIa + ks * 32, 16, 1024, 2)
-                                          : make_smem_desc(sGIa + ks * 32, 16, 512, 4);
-            const uint64_t db = make_smem_desc(sDa + p * C::D_BYTES + ks * 256, 128, (L / 8) * 128, 0);
-            umma_ss(gate, da, db, idesc3, ks > 0);
-          }
-          {  // + 0.5 b2
-            const uint64_t db = make_smem_desc(sW2a + 8 * 256, 128, (kK3 / 8) * 128, 0);
-            umma_ss(gate, dOnes, db, idesc3, 1u);
-          }
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {  // += A3[:, 0:64] . (0.5 W2[:, 0:64])^T   (first E1/E2 group's half)
-            const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
-            umma_ts(gate, tmem + X::HID + ks * 8, db, idesc3, 1u);
-          }
-        }
-        __syncwarp();
-        TR(2, 4, c);
-        // ---- G3, second part: the other group's half of A3
-        mbar_wait_sleep(&bars->e2b_done, c & 1u);
-        tc_fence_after();
-        TR(2, 5, c);
-        if (elect_one_sync()) {
-          const uint32_t gate = tmem + X::GATE0 + p * L;
-#pragma unroll
-          for (int ks = 4; ks < 8; ++ks) {
-            const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
-            umma_ts(gate, tmem + X::HID + 64 + (ks - 4) * 8, db, idesc3, 1u);
-          }
-          umma_commit(&bars->gate_full[p]);
-          if (j == n - 1) umma_commit(&bars->empty[s]);  // last MMA reading this stage's GI rows
-        }
-        __syncwarp();
-        TR(2, 6, c);
-      }
-      ++it;
-    }
-  } else if (warp >= 8 && warp < kCtlWarp0) {
-    // =============================== E1 / E2 groups (g = 0, 1: column halves) ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kXB_Regs));
-    const int g = (warp >> 2) & 1;
-    const int r = tid & 127;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tb = tmem + lane_base;
-    uint32_t ones[8];
-    ones[0] = 0x00003C00u;  // {1.0h, 0}
-#pragma unroll
-    for (int i = 1; i < 8; ++i) ones[i] = 0u;
-
-    // query-image staging (group 0 only): image of query c + 2 goes to sQ[c & 1] once G1(c) is complete
-    uint4 qv[C::QV];
-    auto load_image = [&](int q) __attribute__((always_inline)) {
-      const uint4* src = reinterpret_cast<const uint4*>(P.q_rec + (size_t)q * C::QREC_BYTES);
-#pragma unroll
-      for (int i = 0; i < C::QV; ++i) qv[i] = __ldg(src + r + i * 128);
-    };
-    auto store_image = [&](uint32_t par) __attribute__((always_inline)) {
-#pragma unroll
-      for (int i = 0; i < C::QV; ++i) reinterpret_cast<uint4*>(sQ + par * C::Q_BYTES)[r + i * 128] = qv[i];
-    };
-    // lookahead sequence for the images (runs ahead of the main sequence)
-    FlatSeq qseq(f0, f1, P.bc);
-    int qt = 0, qq = 0;
-    bool qf = false;
-    bool q_have = false;
-    if (g == 0) {
-      // prologue: images of the first two queries, then keep the third in registers
-      q_have = qseq.next(qt, qq, qf);
-      if (q_have) {
-        load_image(qq);
-        store_image(0);
-        q_have = qseq.next(qt, qq, qf);
-        if (q_have) {
-          load_image(qq);
-          store_image(1);
-          q_have = qseq.next(qt, qq, qf);
-          if (q_have) load_image(qq);
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&bars->q0_ready);
-      }
-    }
-
-    // E1 of query `c1` (tile switch first when it opens a tile): LOG -> fp16 -> STASH[c1 & 1] (A operand of G2 and
-    // the logits E3 needs later)
-    FlatSeq seq(f0, f1, P.bc);
-    auto e1 = [&](uint32_t c1, bool first, int it) __attribute__((always_inline)) {
-      if (first) {
-        // tile switch: copy this group's half of the X rows from the landing zone into TMEM.  Every G1 of the previous
-        // tile is complete (this thread has been through E1 of its last query).
-        const int s = it % C::STAGES;
-        mbar_wait_sleep(&bars->full[s], (uint32_t)(it / C::STAGES) & 1u);
-        const unsigned char* xrow = sX + s * C::X_BYTES + r * 128;
-#pragma unroll
-        for (int b = 0; b < X::XB_HALF; ++b) {
-          const int box = g * X::XB_HALF + b;
-          uint32_t v[32];
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {  // undo the 128B TMA swizzle: 16-byte chunk index XOR (row & 7)
-            const uint4 t = *reinterpret_cast<const uint4*>(xrow + box * 16384 + ((ch ^ (r & 7)) << 4));
-            v[4 * ch] = t.x;
-            v[4 * ch + 1] = t.y;
-            v[4 * ch + 2] = t.z;
-            v[4 * ch + 3] = t.w;
-          }
-          tmem_st_x32(tb + X::XT + box * 32, v);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bars->xt_ready);
-      }
-      const uint32_t p = c1 & 1u, k2 = (c1 >> 1) & 1u;
-      if (warp == 8) TR(1, 4, c1);
-      mbar_wait_sleep(&bars->log_full, c1 & 1u);
-      tc_fence_after();
-      if (warp == 8) TR(1, 5, c1);
-      uint32_t la[16], lb[16];
-      tmem_ld_x16(tb + X::LOG + g * LH, la);
-      if constexpr (LH == 32) tmem_ld_x16(tb + X::LOG + g * LH + 16, lb);
-      if (g == 0 && q_have) {  // G1 of this query is complete: sQ[c1 & 1] is free for query c1 + 2
-        store_image(c1 & 1u);
-        fence_proxy_async_smem();
-      }
-      uint32_t pk[LH / 2];
-      tmem_ld_wait_bind16(la);
-      if constexpr (LH == 32) tmem_ld_wait_bind16(lb);
-      tc_fence_before();
-      mbar_arrive(&bars->log_free);  // LOG is in registers (and the next image staged): the next G1 may overwrite it
-#pragma unroll
-      for (int j2 = 0; j2 < 8; ++j2)
-        pk[j2] = pack_f16x2(__uint_as_float(la[2 * j2]), __uint_as_float(la[2 * j2 + 1]));
-      if constexpr (LH == 32) {
-#pragma unroll
-        for (int j2 = 0; j2 < 8; ++j2)
-          pk[8 + j2] = pack_f16x2(__uint_as_float(lb[2 * j2]), __uint_as_float(lb[2 * j2 + 1]));
-      }
-      // the E3 group of parity p must have copied the stash of query c1 - 2 (G2 of that query is long complete)
-      mbar_wait_sleep(&bars->stash_free[p], k2);
-      tc_fence_after();
-      if constexpr (LH == 32) {
-        tmem_st_x16(tb + X::STASH0 + p * (L / 2) + g * (LH / 2), pk);
-      } else {
-        tmem_st_x8(tb + X::STASH0 + p * (L / 2) + g * (LH / 2), pk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&bars->stash_ready[p]);
-      if (g == 0 && q_have) {  // next image into registers
-        q_have = qseq.next(qt, qq, qf);
-        if (q_have) load_image(qq);
-      }
-    };
-    // E2 of query `c2` (this group's 64 hidden units): u -> h = u + u tanh(u) in packed half2 -> A3 (in place)
-    auto e2 = [&](uint32_t c2) __attribute__((always_inline)) {
-      if (warp == 8) TR(1, 0, c2);
-      mbar_wait_sleep(&bars->hid_full, c2 & 1u);
-      tc_fence_after();
-      if (warp == 8) TR(1, 1, c2);
-      uint32_t va[16], vb[16];
-      const uint32_t hid = tb + X::HID + g * 64;
-      auto act = [&](const uint32_t* v, uint32_t col) __attribute__((always_inline)) {
-        uint32_t hk[8];
-#pragma unroll
-        for (int j2 = 0; j2 < 8; ++j2) {
-          const uint32_t u2 = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
-          hk[j2] = fma_f16x2(u2, tanh_f16x2(u2), u2);
-        }
-        tmem_st_x8(hid + col, hk);
-      };
-      // 4 chunks of 16 hidden units, loads one chunk ahead; A3 chunk i (8 columns) lands on HID columns whose fp32
-      // values (chunk i / 2) are already in registers
-      tmem_ld_x16(hid, va);
-      tmem_ld_wait_bind16(va);
-      tmem_ld_x16(hid + 16, vb);
-      act(va, 0);
-      tmem_ld_wait_bind16(vb);
-      tmem_ld_x16(hid + 32, va);
-      act(vb, 8);
-      tmem_ld_wait_bind16(va);
-      tmem_ld_x16(hid + 48, vb);
-      act(va, 16);
-      tmem_ld_wait_bind16(vb);
-      act(vb, 24);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(g == 0 ? &bars->e2a_done : &bars->e2b_done);
-      if (warp == 8) TR(1, 3, c2);
-    };
-    // E1 runs one query ahead of E2, so the G2 of a query executes while this group converts the next query's logits
-    int tile = 0, q = 0;
-    bool first = false;
-    uint32_t c = 0;
-    bool have = seq.next(tile, q, first);
-    if (have) e1(0, first, seq.it);
-    while (have) {
-      have = seq.next(tile, q, first);
-      // (not across a tile boundary: the issuer starts the next tile's first G1 only after this tile's last G3,
-      // which needs E2 of this query)
-      if (have && !first) e1(c + 1, false, seq.it);
-      e2(c);
-      if (have && first) e1(c + 1, true, seq.it);
-      ++c;
-    }
-  } else if (warp < 8) {
-    // =============================== E3 groups (p = 0: even queries, p = 1: odd queries) ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kXA_Regs));
-    const uint32_t p = (uint32_t)(warp >> 2);
-    const int r = tid & 127;
-    const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t gate = tb + X::GATE0 + p * L, stash = tb + X::STASH0 + p * (L / 2);
-    __half* sDw = reinterpret_cast<__half*>(sD + p * C::D_BYTES + (r < L ? nosw_off(r, r, L) : 0));
-    const float2 l2e2 = make_float2(kLog2e, kLog2e);
-    __half gqv = __float2half(0.f);
-    auto load_gq = [&](int q) __attribute__((always_inline)) {
-      if (r < L) gqv = reinterpret_cast<const __half*>(P.q_rec + (size_t)q * C::QREC_BYTES + C::Q_BYTES)[r];
-    };
-    // this group's queries: every other unit of the flat sequence
-    FlatSeq seq(f0, f1, P.bc);
-    int tile = 0, q = 0, tile_n = 0, q_n = 0;
-    bool fdummy = false;
-    auto next_mine = [&](int& t, int& qq) __attribute__((always_inline)) -> bool {
-      int t2, q2;
-      if (!seq.next(t2, q2, fdummy)) return false;  // the other group's query
-      return seq.next(t, qq, fdummy);
-    };
-    bool have;
-    if (p == 0) {
-      have = seq.next(tile, q, fdummy);
-    } else {
-      have = next_mine(tile, q);
-    }
-    if (have) {
-      load_gq(q);
-      if (r < L) *sDw = gqv;  // diag of this group's first query: no G3 has touched the buffer yet
-      fence_proxy_async_smem();
-      mbar_arrive(&bars->gate_free[p]);   // phase 0: GATE[p] free, diag[p] staged
-      mbar_arrive(&bars->stash_free[p]);  // phase 0: STASH[p] free
-    }
-    bool have_n = have && next_mine(tile_n, q_n);
-    if (have_n) load_gq(q_n);
-    uint32_t k = 0;  // this group's queries done
-    while (have) {
-      const float thr_q = P.thr ? __ldg(P.thr + (size_t)q * P.thr_stride) : -CUDART_INF_F;
-      // fp16 logits of this query: copy them out of STASH[p] as soon as E1 has written them, so that E1 of this
-      // group's next query never waits for the stash
-      uint32_t pk[L / 2];
-      mbar_wait_sleep(&bars->stash_ready[p], k & 1u);
-      tc_fence_after();
-      if constexpr (L == 64) {
-        tmem_ld_x32(stash, pk);
-        tmem_ld_wait_bind32(pk);
-      } else {
-        tmem_ld_x16(stash, pk);
-        tmem_ld_wait_bind16(pk);
-      }
-      tc_fence_before();
-      mbar_arrive(&bars->stash_free[p]);
-      if (warp == 0) TR(0, 3, k);
-      mbar_wait_sleep(&bars->gate_full[p], k & 1u);
-      tc_fence_after();
-      if (warp == 0) TR(0, 4, k);
-      float2 num[4], den[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) num[i] = den[i] = make_float2(0.f, 0.f);
-      uint32_t v0[16], v1[16], v2[16];
-      auto gatef = [&](const uint32_t* v, const uint32_t* lgc) __attribute__((always_inline)) {
-#pragma unroll
-        for (int j2 = 0; j2 < 8; ++j2) {
-          const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
-          const float2 a = __fmul2_rn(u, l2e2);
-          const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
-          const float2 x = __ffma2_rn(a, t, a);  // w * log2(e)
-          const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-          den[j2 & 3] = __fadd2_rn(den[j2 & 3], e);
-          num[j2 & 3] = __ffma2_rn(e, __half22float2(*reinterpret_cast<const __half2*>(&lgc[j2])), num[j2 & 3]);
-        }
-      };
-      tmem_ld_x16(gate, v0);
-      tmem_ld_x16(gate + 16, v1);
-      if (have_n) {  // G3 of this query is complete: diag[p] is free for this group's next query
-        if (r < L) *sDw = gqv;
-        fence_proxy_async_smem();
-      }
-      tmem_ld_wait_bind16(v0);
-      tmem_ld_wait_bind16(v1);
-      if constexpr (L == 64) {
-        tmem_ld_x16(gate + 32, v2);
-        gatef(v0, pk);
-        tmem_ld_x16(gate + 48, v0);
-        gatef(v1, pk + 8);
-        tmem_ld_wait_bind16(v2);
-        tmem_ld_wait_bind16(v0);
-        tc_fence_before();
-        mbar_arrive(&bars->gate_free[p]);
-        gatef(v2, pk + 16);
-        gatef(v0, pk + 24);
-      } else {
-        tc_fence_before();
-        mbar_arrive(&bars->gate_free[p]);
-        gatef(v0, pk);
-        gatef(v1, pk + 8);
-      }
-      const float2 n2 = __fadd2_rn(__fadd2_rn(num[0], num[1]), __fadd2_rn(num[2], num[3]));
-      const float2 d2 = __fadd2_rn(__fadd2_rn(den[0], den[1]), __fadd2_rn(den[2], den[3]));
-      const float score = __fdividef(n2.x + n2.y, d2.x + d2.y);
-      if (warp == 0) TR(0, 5, k);
-      const int64_t item = (int64_t)(t0 + tile) * kTile + r;
-      if (item < P.N) {
-        if (P.scores) P.scores[(size_t)q * P.ld + ((int64_t)tile * kTile + r)] = score;
-        if (P.thr && !(score < thr_q)) {  // NaN passes the filter on purpose
-          const int pos = atomicAdd(P.cand_cnt + q, 1);
-          if (pos < P.cand_cap) {
-            P.cand_scores[(size_t)q * P.cand_cap + pos] = score;
-            P.cand_idx[(size_t)q * P.cand_cap + pos] = (int32_t)item;
-          }
-        }
-      }
-      ++k;
-      tile = tile_n;
-      q = q_n;
-      have = have_n;
-      if (have) {
-        have_n = next_mine(tile_n, q_n);
-        if (have_n) load_gq(q_n);
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kCtlWarp0) tmem_dealloc<512>(tmem);
-}
-
-#endif  // MOL_COARSE_XRES
 
 // ------------------------------------------------------------------------------------------------
 // Operand images
@@ -1613,11 +1065,12 @@ __global__ void coarse_weight_images_kernel(const float* __restrict__ w1, const 
 
 // Per query record: block-diagonal zero-padded image of Q_sub / tau (16 rows x K1) followed by 0.5*gq (fp16, l' order).
 __global__ void coarse_query_records_kernel(const float* __restrict__ qsub, const float* __restrict__ gq,
-                                            uint8_t* q_rec, int32_t* overflow, int bc, int PQ, int PX, int d,
-                                            float inv_tau) {
+                                            uint8_t* q_rec, int32_t* overflow, const int32_t* __restrict__ weights_overflow,
+                                            int bc, int PQ, int PX, int d, float inv_tau) {
   const int MG = 16 / PQ, K1 = MG * d, L = PQ * PX;
   const int q = blockIdx.x;
   if (q >= bc) return;
+  if (q == 0 && threadIdx.x == 0 && weights_overflow && *weights_overflow) atomicOr(overflow, 1);
   uint8_t* rec = q_rec + (size_t)q * (16 * K1 * 2 + L * 2);
   for (int i = threadIdx.x; i < 16 * K1; i += blockDim.x) {
     const int row = i / K1, k = i % K1;
@@ -1666,20 +1119,38 @@ bool coarse_supported(const mol_shape_t& s) {
 
 static size_t qrec_bytes(const Dims& D) { return (size_t)16 * (16 / D.Pq) * D.d * 2 + (size_t)D.L * 2; }
 
+void coarse_weight_image_bytes(const mol_shape_t& s, size_t* w1_bytes, size_t* w2_bytes) {
+  Dims D = dims_of(s);
+  *w1_bytes = (size_t)kH * (D.L + 16) * 2;
+  *w2_bytes = (size_t)D.L * kK3 * 2;
+}
+
 void coarse_plan(const mol_shape_t& s, int chunk, Arena& a, CoarseWs* ws) {
   Dims D = dims_of(s);
-  ws->w1_img = a.take<uint8_t>((size_t)kH * (D.L + 16) * 2);
-  ws->w2_img = a.take<uint8_t>((size_t)D.L * kK3 * 2);
   ws->q_rec = a.take<uint8_t>((size_t)chunk * qrec_bytes(D));
   ws->overflow = a.take<int32_t>(1);
 }
 
-int coarse_prepare(const mol_shape_t& s, const mol_weights_t& w, const CoarseWs& ws, cudaStream_t st) {
+// weight images (depend on the weights only: once per weight version through mol_weights_prepare, else per call)
+int coarse_prepare_weights(const mol_shape_t& s, const mol_weights_t& w, uint8_t* w1_img, uint8_t* w2_img,
+                           int32_t* overflow, cudaStream_t st) {
   Dims D = dims_of(s);
-  MOL_CUDA(cudaMemsetAsync(ws.overflow, 0, sizeof(int32_t), st));
   const int n = kH * (D.L + 16) > D.L * kK3 ? kH * (D.L + 16) : D.L * kK3;
-  coarse_weight_images_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.qi_w1, w.qi_b1, w.qi_w2, w.qi_b2, ws.w1_img,
-                                                               ws.w2_img, ws.overflow, D.Pq, D.Px);
+  coarse_weight_images_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.qi_w1, w.qi_b1, w.qi_w2, w.qi_b2, w1_img, w2_img,
+                                                               overflow, D.Pq, D.Px);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
+// per-query operand records of a query chunk (once per chunk; every coarse pass over the chunk reads them).  Resets the
+// chunk's overflow flag and folds the weight-image overflow flag into it.
+int coarse_query_records(const mol_shape_t& s, const CoarseWs& ws, const float* qsub, const float* gq, int bc,
+                         const int32_t* weights_overflow, cudaStream_t st) {
+  Dims D = dims_of(s);
+  if (bc == 0) return MOL_OK;
+  MOL_CUDA(cudaMemsetAsync(ws.overflow, 0, sizeof(int32_t), st));
+  coarse_query_records_kernel<<<bc, 128, 0, st>>>(qsub, gq, ws.q_rec, ws.overflow, weights_overflow, bc, D.Pq, D.Px, D.d,
+                                                  1.0f / s.temperature);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
 }
@@ -1723,15 +1194,11 @@ void* coarse_trace_buffer() { return g_trace; }
 extern "C" void mol_debug_set_trace(void* p) { g_trace = p; }
 
 template <int PX, int DD>
-static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, const float* qsub,
-                         const float* gq, int bc, const CoarseOut& out, cudaStream_t st) {
+static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, int bc, const CoarseOut& out,
+                         cudaStream_t st) {
   using C = CoarseCfg<PX, DD>;
-  Dims D = dims_of(s);
   const int64_t N = ix.num_items;
   const int64_t Np = (N + kTile - 1) / kTile * kTile;
-  coarse_query_records_kernel<<<bc, 128, 0, st>>>(qsub, gq, ws.q_rec, ws.overflow, bc, D.Pq, D.Px, D.d,
-                                                  1.0f / s.temperature);
-  MOL_LAUNCH_CHECK();
   CUtensorMap tmX, tmGI;
   MOL_TRY(encode_2d(&tmX, ix.xsub_half, C::XCOLS, (uint64_t)Np, 64, kTile, CU_TENSOR_MAP_SWIZZLE_128B));
   MOL_TRY(encode_2d(&tmGI, ix.gi_half, C::L, (uint64_t)Np, C::L, kTile,
@@ -1752,17 +1219,18 @@ static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const Coar
   P.ld = out.ld;
   P.tile_begin = out.tile_begin;
   P.tile_end = out.tile_end < 0 ? (int)(Np / kTile) : out.tile_end;
+  P.tile_map = out.tile_map;
   P.bc = bc;
   if (P.tile_end <= P.tile_begin) return MOL_OK;
-#ifdef MOL_COARSE_XRES
-  auto kern = mol_coarse_xres_kernel<PX, DD>;
-#else
   auto kern = mol_coarse_kernel<PX, DD>;
-#endif
-  MOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  int dev = 0, sms = 148;
-  MOL_CUDA(cudaGetDevice(&dev));
-  MOL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static int sms = 0;  // (set once per process: the attribute call and the device query are not free on a 60 us search)
+  if (sms == 0) {
+    MOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    int dev = 0, n = 148;
+    MOL_CUDA(cudaGetDevice(&dev));
+    MOL_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    sms = n;
+  }
   const int64_t F = (int64_t)(P.tile_end - P.tile_begin) * bc;
   int grid = (int)(F < sms ? F : sms);
   if (grid < 1) grid = 1;
@@ -1771,24 +1239,48 @@ static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const Coar
   return MOL_OK;
 }
 
-int coarse_run(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, const float* qsub, const float* gq,
-               int bc, const CoarseOut& out, cudaStream_t st) {
+int coarse_run(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, int bc, const CoarseOut& out,
+               cudaStream_t st) {
   Dims D = dims_of(s);
   if (bc == 0 || ix.num_items == 0) return MOL_OK;
-  if (D.Px == 8 && D.d == 32) return launch_coarse<8, 32>(s, ix, ws, qsub, gq, bc, out, st);
-  if (D.Px == 4 && D.d == 64) return launch_coarse<4, 64>(s, ix, ws, qsub, gq, bc, out, st);
-  if (D.Px == 4 && D.d == 128) return launch_coarse<4, 128>(s, ix, ws, qsub, gq, bc, out, st);
+  if (D.Px == 8 && D.d == 32) return launch_coarse<8, 32>(s, ix, ws, bc, out, st);
+  if (D.Px == 4 && D.d == 64) return launch_coarse<4, 64>(s, ix, ws, bc, out, st);
+  if (D.Px == 4 && D.d == 128) return launch_coarse<4, 128>(s, ix, ws, bc, out, st);
   MOL_CHECK_ARG(false, "tensor-core path does not support this shape");
 }
 
-int coarse_scores(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, const float* qsub,
-                  const float* gq, int bc, float* scores, cudaStream_t st) {
+int coarse_scores(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, int bc, float* scores,
+                  cudaStream_t st) {
   CoarseOut out{};
   out.scores = scores;
   out.ld = ix.num_items;
   out.tile_begin = 0;
   out.tile_end = -1;
-  return coarse_run(s, ix, ws, qsub, gq, bc, out, st);
+  return coarse_run(s, ix, ws, bc, out, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strided sample: logical -> physical tile tables of the threshold pass (tiles 0, stride, 2 stride, ...) and of the
+// main pass (every other tile, in order).
+// ------------------------------------------------------------------------------------------------
+__global__ void tile_maps_kernel(int32_t* __restrict__ sample_map, int32_t* __restrict__ main_map, int tiles, int stride,
+                                 int count) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // physical tile
+  if (t >= tiles) return;
+  const bool is_sample = (t % stride == 0) && (t / stride < count);
+  if (is_sample) {
+    sample_map[t / stride] = t;
+  } else {
+    const int before = t / stride < count ? t / stride + 1 : count;  // sample tiles in [0, t)
+    main_map[t - before] = t;
+  }
+}
+
+int coarse_tile_maps(int32_t* sample_map, int32_t* main_map, int tiles, int stride, int count, cudaStream_t st) {
+  if (tiles <= 0) return MOL_OK;
+  tile_maps_kernel<<<(tiles + 255) / 256, 256, 0, st>>>(sample_map, main_map, tiles, stride, count);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1796,7 +1288,7 @@ int coarse_scores(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& w
 // ------------------------------------------------------------------------------------------------
 __global__ void filter_matrix_kernel(const float* __restrict__ scores, int64_t n, int64_t ld, const float* __restrict__ thr,
                                      int thr_stride, int32_t* __restrict__ cnt, float* __restrict__ cand_scores,
-                                     int32_t* __restrict__ cand_idx, int cap) {
+                                     int32_t* __restrict__ cand_idx, int cap, int tile_stride) {
   const int b = blockIdx.y;
   const float t = thr[(size_t)b * thr_stride];
   const float* row = scores + (size_t)b * ld;
@@ -1806,19 +1298,22 @@ __global__ void filter_matrix_kernel(const float* __restrict__ scores, int64_t n
       const int pos = atomicAdd(cnt + b, 1);
       if (pos < cap) {
         cand_scores[(size_t)b * cap + pos] = v;
-        cand_idx[(size_t)b * cap + pos] = (int32_t)i;
+        // column -> item: the matrix holds the tiles 0, tile_stride, 2 tile_stride, ... of the corpus (strided sample)
+        cand_idx[(size_t)b * cap + pos] = (int32_t)((i >> 7) * tile_stride * 128 + (i & 127));
       }
     }
   }
 }
 
 int coarse_filter_matrix(const float* scores, int64_t n, int64_t ld, int bc, const float* thr, int thr_stride,
-                         int32_t* cnt, float* cand_scores, int32_t* cand_idx, int cap, cudaStream_t st) {
+                         int32_t* cnt, float* cand_scores, int32_t* cand_idx, int cap, int tile_stride,
+                         cudaStream_t st) {
   if (bc == 0 || n == 0) return MOL_OK;
   int64_t gx = (n + 1023) / 1024;
   if (gx > 64) gx = 64;
   dim3 grid((unsigned)gx, (unsigned)bc);
-  filter_matrix_kernel<<<grid, 256, 0, st>>>(scores, n, ld, thr, thr_stride, cnt, cand_scores, cand_idx, cap);
+  filter_matrix_kernel<<<grid, 256, 0, st>>>(scores, n, ld, thr, thr_stride, cnt, cand_scores, cand_idx, cap,
+                                             tile_stride < 1 ? 1 : tile_stride);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
 }
@@ -1826,11 +1321,14 @@ int coarse_filter_matrix(const float* scores, int64_t n, int64_t ld, int bc, con
 // ------------------------------------------------------------------------------------------------
 // Safety check: one warp per query.
 // ------------------------------------------------------------------------------------------------
+// margin of the acceptance test, in units of the largest coarse-vs-exact difference seen on the query's own candidates
+// (what this test does and does not prove)
+constexpr float kSafetyErrFactor = 3.0f, kSafetyErrAbs = 2e-2f;
 __global__ void safety_flags_kernel(const float* __restrict__ cand, const float* __restrict__ exact,
                                     const float* __restrict__ topk, int bc, int kk, int k,
                                     const int32_t* __restrict__ ovf_a, const int32_t* __restrict__ ovf_b,
                                     const int32_t* __restrict__ cnt, const float* __restrict__ thr, int thr_stride,
-                                    int cap, int32_t* __restrict__ flags) {
+                                    int cap, int32_t* __restrict__ flags, int32_t* __restrict__ stats) {
   int b = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
   int lane = threadIdx.x % 32;
   if (b >= bc) return;
@@ -1856,21 +1354,28 @@ __global__ void safety_flags_kernel(const float* __restrict__ cand, const float*
       const int c = cnt[b];
       if (c > cap) bad = true;                              // survivors were dropped
       if (c <= kk) cmin = thr[(size_t)b * thr_stride];      // every survivor is a candidate: outsiders are below thr
+      if (stats) {
+        if (c > cap) atomicAdd(stats + 1, 1);
+        if (c < kk) atomicAdd(stats + 5, 1);
+        atomicMax(stats + 2, c);
+      }
     }
     // NaN-safe: anything but a provable "no" flags the query for the exact fallback
-    flags[b] = (!bad && cmin + 1.5f * err + 1e-3f < sk) ? 0 : 1;
+    const int f = (!bad && cmin + kSafetyErrFactor * err + kSafetyErrAbs < sk) ? 0 : 1;
+    flags[b] = f;
+    if (stats && f) atomicAdd(stats + 0, 1);
   }
 }
 
 int coarse_safety_flags(const float* cand_scores, const float* exact_scores, const float* topk_scores,
                         int bc, int kk, int k, const int32_t* overflow_a, const int32_t* overflow_b,
                         const int32_t* cnt, const float* thr, int thr_stride, int cap, int32_t* flags,
-                        cudaStream_t st) {
+                        int32_t* stats, cudaStream_t st) {
   if (bc == 0) return MOL_OK;
   int threads = bc * 32;
   safety_flags_kernel<<<(threads + 255) / 256, 256, 0, st>>>(cand_scores, exact_scores, topk_scores, bc, kk, k,
                                                              overflow_a, overflow_b, cnt, thr, thr_stride, cap,
-                                                             flags);
+                                                             flags, stats);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
 }

@@ -62,6 +62,7 @@ class PackedWeights:
     """fp32, contiguous, device-resident views/copies of the module's parameters + the C structs."""
 
     def __init__(self, state: Dict[str, torch.Tensor], shape: MolShape, device: torch.device) -> None:
+        device = torch.device(device)
         self.device = device
         self.shape = shape
         self.keep: List[torch.Tensor] = []
@@ -75,6 +76,19 @@ class PackedWeights:
             if key not in state:
                 raise ValueError(f"MoL weights: missing parameter {key}")
             self.struct.uid_emb[i] = self._dev(state[key]).data_ptr()
+        self.struct.prepared = None
+        self.prepared: Optional[torch.Tensor] = None
+        if device.type == "cuda":
+            # operands that depend on the weights alone (transposed qi-MLP, fp16 UMMA images): once per weight version
+            lib = _lib.load()
+            nbytes = c_size_t()
+            _lib.check(lib.mol_weights_prepared_bytes(byref(shape), byref(nbytes)))
+            self.prepared = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=device)
+            base = (self.prepared.data_ptr() + 255) // 256 * 256
+            with torch.cuda.device(device):
+                _lib.check(lib.mol_weights_prepare(byref(shape), byref(self.struct), ctypes.c_void_p(base), nbytes.value,
+                                                   _stream_ptr(device)))
+            self.struct.prepared = base
 
     def _dev(self, t: torch.Tensor) -> torch.Tensor:
         t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
@@ -183,6 +197,17 @@ def search(
             )
         )
     return out_s, out_i
+
+
+def search_stats(workspace: Workspace) -> Dict[str, int]:
+    """Counters of the last search that used `workspace` (mol_search_stats; synchronises the stream)."""
+    lib = _lib.load()
+    if workspace.buf is None:
+        raise RuntimeError("no search has used this workspace yet")
+    out = (c_int32 * _lib.NUM_STATS)()
+    with torch.cuda.device(workspace.device):
+        _lib.check(lib.mol_search_stats(_ptr(workspace.buf), out, _stream_ptr(workspace.device)))
+    return dict(zip(_lib.STAT_NAMES, (int(v) for v in out)))
 
 
 def search_host(
@@ -299,6 +324,36 @@ def merge_topk(part_scores: torch.Tensor, part_ids: torch.Tensor, k: int) -> Tup
         _lib.check(
             lib.mol_merge_topk(_ptr(ps), _ptr(pi), R, B, k, _ptr(out_s), _ptr(out_i), _ptr(ws), ws.numel(), _stream_ptr(dev))
         )
+    return out_s, out_i
+
+
+def pack_topk(scores: torch.Tensor, ids: torch.Tensor, k: int) -> torch.Tensor:
+    """(B, k_valid <= k) partial list -> (B, k) packed entries (uint8 (B, k, 16)) for the single all-gather."""
+    lib = _lib.load()
+    _require_cuda(scores, "scores")
+    B, kv = scores.shape
+    s = scores.detach().to(torch.float32).contiguous()
+    i = ids.detach().to(torch.int64).contiguous()
+    out = torch.empty((B, k, _lib.MOL_PACKED_ENTRY_BYTES), dtype=torch.uint8, device=scores.device)
+    with torch.cuda.device(scores.device):
+        _lib.check(lib.mol_pack_topk(_ptr(s), _ptr(i), B, kv, k, _ptr(out), _stream_ptr(scores.device)))
+    return out
+
+
+def merge_topk_packed(gathered: torch.Tensor, R: int, B: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """gathered (R, B, k, 16) uint8 packed entries -> global (B, k) scores / ids (mol_merge_topk_packed)."""
+    lib = _lib.load()
+    _require_cuda(gathered, "gathered")
+    dev = gathered.device
+    assert gathered.is_contiguous() and gathered.numel() == R * B * k * _lib.MOL_PACKED_ENTRY_BYTES
+    out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+    nbytes = c_size_t()
+    _lib.check(lib.mol_merge_topk_packed_workspace_bytes(R, B, k, byref(nbytes)))
+    ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mol_merge_topk_packed(_ptr(gathered), R, B, k, _ptr(out_s), _ptr(out_i), _ptr(ws), ws.numel(),
+                                             _stream_ptr(dev)))
     return out_s, out_i
 
 

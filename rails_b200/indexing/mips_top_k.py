@@ -28,16 +28,31 @@ class MIPSBruteForceTopK(MIPSTopKModule):
     def __init__(self, item_embeddings: torch.Tensor, item_ids: torch.Tensor) -> None:
         super().__init__(item_embeddings=item_embeddings, item_ids=item_ids)
         # the C ABI wants (X, D) row-major fp32 (the reference keeps the (D, X) transpose for torch.mm)
-        self._items = item_embeddings.squeeze(0).detach().to(torch.float32).contiguous()
-        self._ids = item_ids.reshape(-1).detach().to(torch.int64).contiguous()
+        self._items = None
+        self._ids = None
+        self._key = None
         self._ws = None
+        if item_embeddings.is_cuda:
+            self._sync()
+
+    def _sync(self) -> None:
+        """(X, D) fp32 items and int64 ids on the items' device, rebuilt when the source tensors change in place (the
+        reference reads `self._item_embeddings` on every call).  k is limited to MOL_MAX_K = 8192 by the select kernels
+        (torch.topk accepts any k <= X)."""
+        e, i = self._item_embeddings, self._item_ids
+        key = (e.data_ptr(), e._version, tuple(e.shape), i.data_ptr(), i._version)
+        if self._key != key:
+            self._items = e.squeeze(0).detach().to(torch.float32).contiguous()
+            self._ids = i.reshape(-1).detach().to(device=self._items.device, dtype=torch.int64).contiguous()
+            self._key = key
 
     @torch.no_grad()
     def forward(self, query_embeddings: torch.Tensor, k: int, sorted: bool = True, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
         """(B, D) queries -> (top_k_scores (B, k), top_k_ids (B, k) int64); results are always sorted."""
         lib = _lib.load()
         engine._require_cuda(query_embeddings, "query_embeddings")
-        engine._require_cuda(self._items, "item_embeddings")
+        engine._require_cuda(self._item_embeddings, "item_embeddings")
+        self._sync()
         dev = self._items.device
         q = query_embeddings.detach().to(device=dev, dtype=torch.float32).contiguous()
         B, D = int(q.size(0)), int(q.size(1))
@@ -53,7 +68,7 @@ class MIPSBruteForceTopK(MIPSTopKModule):
         with torch.cuda.device(dev):
             _lib.check(
                 lib.mol_mips_search(
-                    engine._ptr(self._items), engine._ptr(self._ids.to(dev)), engine._ptr(q), N, D, B, int(k),
+                    engine._ptr(self._items), engine._ptr(self._ids), engine._ptr(q), N, D, B, int(k),
                     engine._ptr(out_s), engine._ptr(out_i), engine._ptr(self._ws), self._ws.numel(),
                     engine._stream_ptr(dev),
                 )

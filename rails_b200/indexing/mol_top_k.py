@@ -5,9 +5,11 @@ Same constructor, same `forward(query_embeddings, k, sorted=True, **kwargs) -> (
 ids (B,k) int64)`.  What differs is where the work happens: the item side (projection, l2-norm,
 item-only gating MLP) is computed ONCE into an on-device index at construction (the reference
 recomputes it over the whole corpus on every call), and each forward() is one `mol_search` call of
-libmol_b200.so: CUDA query prologue -> tcgen05 coarse scoring pass (bf16 operands, fp32 accumulate)
--> radix-select of the K' best per query -> exact fp32 rescoring -> final sorted top-k (+ automatic
-exact fallback for any query whose candidate set cannot be proven complete).
+libmol_b200.so: CUDA query prologue -> tcgen05 coarse scoring pass (fp16 operands, fp32 accumulate)
+with the candidate filter fused into its epilogue -> the K' best candidates per query -> exact fp32
+rescoring -> final sorted top-k.  A query whose candidate set fails the acceptance test (an empirical
+margin between the coarse and the exact scores, DESIGN.md 4.3) is re-done by the exact fp32 kernel;
+`mode=MODE_EXACT` scores every pair in fp32 and is the path with an unconditional guarantee.
 """
 from __future__ import annotations
 

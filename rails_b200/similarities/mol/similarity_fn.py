@@ -130,7 +130,7 @@ class MoLSimilarity(SimilarityModule):
         self._packed: Optional[engine.PackedWeights] = None
         self._packed_key = None
         self._workspaces: Dict[torch.device, engine.Workspace] = {}
-        self._index_cache = None  # (key, IndexHandle) of the last forward()'s item tensor
+        self._index_cache = None  # (item tensor, key, IndexHandle) of the last forward()
 
     # ------------------------------------------------------------------ engine plumbing
     def mol_shape(self) -> MolShape:
@@ -197,6 +197,12 @@ class MoLSimilarity(SimilarityModule):
             self._index_cache = None
         return self._packed
 
+    def invalidate_index_cache(self) -> None:
+        """Drops the cached weights / item-side index (needed only after edits through `.data`, which `_version` misses)."""
+        self._packed = None
+        self._packed_key = None
+        self._index_cache = None
+
     def workspace(self, device: torch.device) -> engine.Workspace:
         if device not in self._workspaces:
             self._workspaces[device] = engine.Workspace(device)
@@ -254,9 +260,14 @@ class MoLSimilarity(SimilarityModule):
             )
         dev = query_embeddings.device
         weights = self.packed_weights(dev)
-        key = (item_embeddings.data_ptr(), item_embeddings._version, tuple(item_embeddings.shape), self._packed_key)
-        if self._index_cache is None or self._index_cache[0] != key:
-            self._index_cache = (key, engine.IndexHandle(weights, item_embeddings.squeeze(0), None))
-        index = self._index_cache[1]
+        # The item-side cache is reused while the caller passes the SAME tensor object, unmodified (in-place edits bump
+        # `_version`; edits through `.data` do not - call `invalidate_index_cache()` after those).  The entry keeps a
+        # strong reference to that tensor, so its address cannot be handed to another tensor while the entry lives.
+        key = (item_embeddings._version, tuple(item_embeddings.shape), item_embeddings.dtype, self._packed_key)
+        c = self._index_cache
+        if c is None or c[0] is not item_embeddings or c[1] != key:
+            c = (item_embeddings, key, engine.IndexHandle(weights, item_embeddings.squeeze(0), None))
+            self._index_cache = c
+        index = c[2]
         scores = engine.score_all(weights, index, self.workspace(dev), query_embeddings, kwargs.get("user_ids"))
         return scores.to(query_embeddings.dtype), {}

@@ -38,7 +38,7 @@ def test_default_build_reports_the_shipped_kernel_knobs():
     if os.environ.get("MOL_B200_LIB"):
         pytest.skip("a tuning variant is loaded")
     k = _lib.build_knobs()
-    assert k == {"e2poly": 0x0E, "e2h2": 0, "e3poly": 0, "e3h2": 0, "h2lite": 0, "ex2emu": 0, "e2share": 0, "g1late": 0}
+    assert k == {"e2poly": 0, "e2h2": 0x3E, "e3poly": 0, "e3h2": 0, "h2lite": 0, "ex2emu": 0, "e2share": 0, "g1late": 0}
 
 
 def test_constants_match_header():
@@ -51,7 +51,7 @@ def test_constants_match_header():
 
 def test_struct_layouts():
     assert ctypes.sizeof(_lib.MolShape) == 4 * (11 + 4 + 1) + 8
-    assert ctypes.sizeof(_lib.MolWeights) == 8 * (16 + 4)
+    assert ctypes.sizeof(_lib.MolWeights) == 8 * (16 + 4 + 1)  # + `prepared`
     assert ctypes.sizeof(_lib.MolIndex) == 8 * 8
 
 
@@ -138,12 +138,24 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 
 def test_product_code_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "rails_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                src = open(os.path.join(dirpath, f)).read()
-                assert "import oracle" not in src and "from oracle" not in src, f
+    for pkg in (os.path.join(ROOT, "rails_b200"), os.path.join(ROOT, "rails"), os.path.join(ROOT, "include")):
+        for dirpath, _, files in os.walk(pkg):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert "import oracle" not in src and "from oracle" not in src, f
+                    assert "tests." not in src or f == "workloads.py", f
+
+
+def test_rails_alias_package_is_the_same_modules():
+    """the replacement classes are importable under the reference's module paths."""
+    import rails  # noqa: F401
+    from rails.indexing.mol_top_k import MoLBruteForceTopK
+    from rails.similarities.mol.similarity_fn import MoLSimilarity
+    from rails_b200.indexing import mol_top_k
+    from rails_b200.similarities.mol import similarity_fn
+
+    assert MoLBruteForceTopK is mol_top_k.MoLBruteForceTopK and MoLSimilarity is similarity_fn.MoLSimilarity
 
 
 def test_get_top_k_module_names_match_the_reference():

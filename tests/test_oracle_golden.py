@@ -44,3 +44,16 @@ def test_chunked_equals_unchunked():
     a = O.brute_force_top_k(g["cfg"], g["sd"], g["queries"], g["items"], g["item_ids"], 50)
     b = O.brute_force_top_k(g["cfg"], g["sd"], g["queries"], g["items"], g["item_ids"], 50, chunk=5)
     assert torch.equal(a[1], b[1])
+
+
+def test_oracle_matches_reference_on_the_large_fixture():
+    """150k-item corpus (the size class of the CUDA path's fused candidate filter): the reference's top-200 and a strided
+    sample of its score matrix, reproduced by the oracle from seed-regenerated items."""
+    from tests.golden_util import load_large
+
+    g = load_large()
+    top_s, top_ids, scores = O.brute_force_top_k(g["cfg"], g["sd"], g["queries"], g["items"], g["item_ids"], g["k"], chunk=2)
+    assert (scores[:, :: g["col_stride"]] - g["ref_scores_strided"]).abs().max().item() <= 2e-6
+    r = O.compare_top_k(g["ref_top_scores"], g["ref_top_ids"], scores, g["item_ids"], g["k"], 1e-5, 1e-5)
+    assert r["ok"] == 1.0, r
+    assert torch.equal(top_ids, g["ref_top_ids"])
