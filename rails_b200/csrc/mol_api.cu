@@ -299,6 +299,12 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
     ws->fidx = nullptr;
     ws->map_sample = ws->map_main = nullptr;
   }
+  if (tensor) {  // the coarse kernel walks its (tile, query) units in 32-bit arithmetic
+    const int64_t tiles = (N + 127) / 128;
+    const int64_t max_rows = tiles > 0 ? ((1ll << 31) - 1) / tiles : ws->chunk;
+    if (ws->chunk > max_rows) ws->chunk = (int)(max_rows < 1 ? 1 : max_rows);
+    if (ws->chunk_fb > ws->chunk) ws->chunk_fb = ws->chunk;
+  }
   ws->cand_scores = a.take<float>((size_t)ws->chunk * ws->Kp);
   ws->cand_idx = a.take<int32_t>((size_t)ws->chunk * ws->Kp);
   ws->exact_scores = a.take<float>((size_t)ws->chunk * ws->Kp);

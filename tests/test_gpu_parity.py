@@ -576,7 +576,7 @@ def _nccl_worker(rank, world, port, out):
 
     import torch.distributed as dist
 
-    from rails_b200.indexing.sharded_top_k import ShardedMoLBruteForceTopK, shard_range
+    from rails_b200.indexing.sharded_top_k import ReplicatedMoLBruteForceTopK, ShardedMoLBruteForceTopK, shard_range
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -593,7 +593,17 @@ def _nccl_worker(rank, world, port, out):
         s, i = ShardedMoLBruteForceTopK(local, hi - lo)(q, k)
         full = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0))
         rs, ri = full(q, k)
-        out[rank] = bool(torch.equal(i, ri)) and bool(torch.equal(s, rs))
+        ok = bool(torch.equal(i, ri)) and bool(torch.equal(s, rs))
+        # query-split layout over the replicated corpus (ragged: 15 queries over 2 ranks)
+        s2, i2 = ReplicatedMoLBruteForceTopK(full)(q[:15], k)
+        ok = ok and bool(torch.equal(i2, ri[:15])) and bool(torch.equal(s2, rs[:15]))
+        # k beyond the corpus: RuntimeError on every rank, before any collective
+        try:
+            ShardedMoLBruteForceTopK(local, hi - lo)(q, N + 1)
+            ok = False
+        except RuntimeError as e:
+            ok = ok and "out of range" in str(e)
+        out[rank] = ok
     finally:
         dist.destroy_process_group()
 
