@@ -52,6 +52,12 @@ constexpr int kThreads = kEpiThreads + 4 * 32;
 #ifndef MOL_COARSE_V3
 #define MOL_COARSE_V3 0
 #endif
+#ifndef MOL_HID_F16
+#define MOL_HID_F16 1  // measured (round 2): 33.2 -> 32.4 ms per 512 x 1M step, max coarse-vs-exact error 0.023 -> 0.026
+#endif
+// HID accumulates in fp16 (kind::f16 with an F16 D) and E2 reads it with tcgen05.ld ... .pack::16b: no f32 -> f16x2
+// conversions and half the load registers in E2, at the price of five fp16 roundings of the hidden pre-activation
+constexpr bool kHidF16 = MOL_HID_F16 != 0;
 #ifndef MOL_E2_REGS
 #define MOL_E2_REGS 56
 #endif
@@ -359,6 +365,14 @@ __device__ __forceinline__ void e2_act_chunk(const uint32_t* v, uint32_t taddr, 
   tmem_st_x8(taddr, hk);
 }
 
+// The same chunk from eight PACKED fp16 pairs (fp16 HID accumulator read with .pack::16b).
+__device__ __forceinline__ void e2_act_chunk_packed(const uint32_t* u2, uint32_t taddr, bool h2) {
+  uint32_t hk[8];
+#pragma unroll
+  for (int j2 = 0; j2 < 8; ++j2) hk[j2] = h2 ? silu2_h2(u2[j2]) : fma_f16x2(u2[j2], tanh_f16x2(u2[j2]), u2[j2]);
+  tmem_st_x8(taddr, hk);
+}
+
 template <int PX, int DD>
 __global__ void __launch_bounds__(kThreads, 1)
 mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmGI,
@@ -445,7 +459,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     {
       const int wg = warp - kCtlWarp0;
       constexpr uint32_t idesc1 = make_idesc_f16(128, 16);
-      constexpr uint32_t idesc2 = make_idesc_f16(128, kH);
+      constexpr uint32_t idesc2 = kHidF16 ? make_idesc_f16_acc16(128, kH) : make_idesc_f16(128, kH);
       constexpr uint32_t idesc3 = make_idesc_f16(128, L);
       const uint32_t sW1a = smem_u32(sW1), sW2a = smem_u32(sW2);
       const uint32_t sQa = smem_u32(sQ + wg * C::Q_BYTES), sDa = smem_u32(sD + wg * C::D_BYTES);
@@ -719,6 +733,26 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       // 8 chunks of 16 hidden units, loads one chunk ahead; A3 chunk c (8 columns) overwrites HID columns that
       // chunk c/2 (already in registers) came from
       constexpr int nE2 = 8 - kE2Share;  // chunks [nE2, 8) are converted by the slot's E3 warpgroup (MOL_E2_SHARE)
+      if constexpr (kHidF16) {
+        static_assert(!kHidF16 || (kE2Poly64 == 0 && kE2Share == 0), "MOL_HID_F16 supports the MUFU / half2 chunk forms only");
+        // packed loads, two chunks ahead (8 registers per chunk)
+        uint32_t p0[8], p1[8], p2[8];
+        tmem_ld_x8_pack16(base + kColHid, p0);
+        tmem_ld_x8_pack16(base + kColHid + 16, p1);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t* cur = (c % 3 == 0) ? p0 : (c % 3 == 1) ? p1 : p2;
+          uint32_t* nxt = ((c + 2) % 3 == 0) ? p0 : ((c + 2) % 3 == 1) ? p1 : p2;
+          tmem_ld_wait_bind8(cur);
+          if (c + 2 < 8) tmem_ld_x8_pack16(base + kColHid + 16 * (c + 2), nxt);
+          e2_act_chunk_packed(cur, base + kColHid + 8 * c, ((kE2H2Mask >> c) & 1u) != 0);
+          if (c == 3) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars->e2a_done[wg]);
+          }
+        }
+      } else {
       tmem_ld_x16(base + kColHid, va);
 #pragma unroll
       for (int c = 0; c < 8; c += 2) {
@@ -740,6 +774,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           if (warp == 4) TR(1, 2, cnt);
           if (e1_early) do_e1(cnt + 1);  // (va, prefetched for chunk 4, stays live across it)
         }
+      }
       }
       tmem_st_x8(base + kColHid + 64, ones);
       tmem_st_wait();
@@ -837,9 +872,17 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     int map_tile = -1, map_phys = 0;
     // E3 of query (tile_p, q_p) (gate_full phase `par`).  Once GATE is in registers it stages the diag of the next
     // query in sequence (if any: its G3 is the next writer of GATE and the next reader of the diag) and releases both.
-    auto e3 = [&](const uint32_t (&pk)[L / 2], int tile_p, int q_p, uint32_t par, bool stage_diag) __attribute__((always_inline)) {
-      // the filter threshold of this query: loaded now, used after the weighted sum
-      const float thr_q = P.thr ? __ldg(P.thr + (size_t)q_p * P.thr_stride) : -CUDART_INF_F;
+    // pf_img / pf_gq: queries whose image / 0.5 gq are prefetched from global memory (-1: none).  The loads are issued
+    // right BEHIND the gate_free arrive: an mbarrier arrive (release) waits for the thread's outstanding loads, so a
+    // prefetch in front of it turns its whole latency into a stall (round-2 stage traces).
+    auto e3 = [&](const uint32_t (&pk)[L / 2], int tile_p, int q_p, uint32_t par, bool stage_diag, int pf_img, int pf_gq)
+                  __attribute__((always_inline)) {
+      float thr_q = -CUDART_INF_F;
+      auto prefetch = [&]() __attribute__((always_inline)) {
+        if (P.thr) thr_q = __ldg(P.thr + (size_t)q_p * P.thr_stride);  // used after the weighted sum
+        if (pf_img >= 0) load_image(pf_img);
+        if (pf_gq >= 0) load_gq(pf_gq);
+      };
       if (warp == 0) TR(0, 3, cnt - 1u);
       mbar_wait_sleep(&bars->gate_full[wg], par);
       tc_fence_after();
@@ -929,6 +972,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tc_fence_before();
           mbar_arrive(&bars->gate_free[wg]);
         }
+        prefetch();
         gate(v2, pk + 16);
         gate(v0, pk + 24);
       } else {
@@ -936,6 +980,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tc_fence_before();
           mbar_arrive(&bars->gate_free[wg]);
         }
+        prefetch();
         gate(v0, pk);
         gate(v1, pk + 8);
       }
@@ -994,11 +1039,12 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       e1(pk_cur);
       int tile_nn = 0, q_nn = 0;
       const bool have_nn = have_n && seq.next(tile_nn, q_nn);
-      if (have_nn) load_image(q_nn);  // image of the query after next (qv was stored to smem inside e1)
       if (have_p) {
-        // E3(prev) stages diag(cur) from gqv, which currently holds gq(cur)
-        e3(pk_prev, tile_p, q_p, (cnt - 1u) & 1u, true);
-        if (have_n) load_gq(q_n);  // gq(next), staged by the next step's E3
+        // E3(prev) stages diag(cur) from gqv, which currently holds gq(cur); behind its gate_free arrive it prefetches the
+        // image of the query after next (qv was stored to smem inside e1) and gq(next), staged by the next step's E3
+        e3(pk_prev, tile_p, q_p, (cnt - 1u) & 1u, true, have_nn ? q_nn : -1, have_n ? q_n : -1);
+      } else if (have_nn) {
+        load_image(q_nn);
       }
       e2_share();  // (no-op unless MOL_E2_SHARE)
       ++cnt;
@@ -1015,12 +1061,12 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     while (have) {
       step(pkA, pkB);
       if (!have) {
-        e3(pkA, tile_p, q_p, (cnt - 1u) & 1u, false);
+        e3(pkA, tile_p, q_p, (cnt - 1u) & 1u, false, -1, -1);
         break;
       }
       step(pkB, pkA);
       if (!have) {
-        e3(pkB, tile_p, q_p, (cnt - 1u) & 1u, false);
+        e3(pkB, tile_p, q_p, (cnt - 1u) & 1u, false, -1, -1);
         break;
       }
     }
@@ -1192,7 +1238,7 @@ static void* g_trace = nullptr;
 const char* coarse_build_knobs() {
   return "e2poly=" MOL_STR(MOL_E2_POLY_MASK) " e2h2=" MOL_STR(MOL_E2_H2_MASK) " e3poly=" MOL_STR(MOL_E3_POLY_OF4)
          " e3h2=" MOL_STR(MOL_E3_H2_OF4) " h2lite=" MOL_STR(MOL_H2_LITE) " ex2emu=" MOL_STR(MOL_EX2_EMU_OF4)
-         " e2share=" MOL_STR(MOL_E2_SHARE) " g1late=" MOL_STR(MOL_G1_LATE);
+         " e2share=" MOL_STR(MOL_E2_SHARE) " g1late=" MOL_STR(MOL_G1_LATE) " hidf16=" MOL_STR(MOL_HID_F16);
 }
 
 void* coarse_trace_buffer() { return g_trace; }

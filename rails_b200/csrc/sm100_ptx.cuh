@@ -127,6 +127,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);  // M >> 4
 }
 
+// kind::f16 instruction descriptor with an F16 accumulator: F16 x F16 -> F16 (D format field 0).  A 16-bit accumulator
+// still takes one TMEM column per element; tcgen05.ld ... .pack::16b reads two adjacent columns into one register.
+__host__ __device__ constexpr uint32_t make_idesc_f16_acc16(int M, int N) {
+  return ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // One lane of a converged warp (warp-uniform predicate: lets ptxas keep the MMA operands in uniform registers).
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred = 0;
@@ -232,6 +238,19 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
+               : "memory");
+}
+// 16 columns of 16-bit accumulators -> 8 registers of packed pairs (column 2i in the low half of register i)
+__device__ __forceinline__ void tmem_ld_x8_pack16(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_bind8(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
