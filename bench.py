@@ -261,6 +261,20 @@ def time_search(engine, weights, index, wsp, q, uid, k, mode, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
+def time_module(top, q, k, kw, steps, warmup):
+    """ms per forward() of a top-k module (the public call, output tensors included)."""
+    for _ in range(warmup):
+        top(q, k=k, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        top(q, k=k, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
 def secondary_block(dev, mode, north=None):
     """BASELINE.json configs 1-3 and the B sweep of SURVEY.md §8(d) (1M items, top-100), a few timed steps each."""
     from rails_b200 import engine
@@ -281,6 +295,12 @@ def secondary_block(dev, mode, north=None):
         out[name] = {"workload": workload_name(label, N, B, k), "ms_per_step": ms, "queries_per_s": B / (ms * 1e-3),
                      "tflops_algorithmic": B * N * flops_per_pair(cfg) / (ms * 1e-3) / 1e12,
                      "hbm_gbs_algorithmic": N * bytes_per_item(cfg) / (ms * 1e-3) / 1e9}
+        if B <= 128:  # launch-bound configs: the same call replayed as one CUDA graph (MoLBruteForceTopK(cuda_graph=True))
+            gtop = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=mode, cuda_graph=True)
+            kw = {} if uid is None else {"user_ids": uid}
+            gms = time_module(gtop, q, k, kw, 50, 5)
+            out[name]["cuda_graph"] = {"ms_per_step": gms, "queries_per_s": B / (gms * 1e-3)}
+            del gtop
         del top, items
     if north is not None:
         weights, index, wsp, q_dev, k = north
@@ -291,6 +311,22 @@ def secondary_block(dev, mode, north=None):
             ms = time_search(engine, weights, index, wsp, q_dev[:b].contiguous(), None, k, mode, 10 if b >= 128 else 30, 3)
             sweep[str(b)] = {"ms_per_step": ms, "queries_per_s": b / (ms * 1e-3),
                              "hbm_gbs_algorithmic": index.N * 640 / (ms * 1e-3) / 1e9}
+            if b <= 32:
+                g = engine.GraphedSearch(weights, index, b, k, mode, False)
+                qb = q_dev[:b].contiguous()
+                for _ in range(5):
+                    g(qb, None)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(30):
+                    g(qb, None)
+                e1.record()
+                torch.cuda.synchronize()
+                gms = e0.elapsed_time(e1) / 30
+                sweep[str(b)]["cuda_graph"] = {"ms_per_step": gms, "queries_per_s": b / (gms * 1e-3),
+                                               "hbm_gbs_algorithmic": index.N * 640 / (gms * 1e-3) / 1e9}
+                del g
         out["batch_sweep_1m_top100"] = sweep
     return out
 

@@ -212,6 +212,19 @@ static bool use_tensor(const mol_shape_t& s, int mode) {
 }
 
 constexpr int64_t kFilterMinItems = 1 << 16;
+// ... and only for batches whose (B, N) coarse score matrix would cost more to write and select from than the threshold
+// pass does (sample pass + two selections + filter launches ~ 50 us): below 2^24 pairs (64 MB of fp32 scores) the matrix
+// strategy is one coarse launch + one segmented select
+constexpr int64_t kFilterMinPairs = 1ll << 24;
+// (MOL_B200_FILTER_MIN_PAIRS overrides it, so that tests reach the filter strategy with a handful of queries)
+static int64_t filter_min_pairs() {
+  const char* e = getenv("MOL_B200_FILTER_MIN_PAIRS");
+  if (e) {
+    const long long v = atoll(e);
+    if (v >= 0) return (int64_t)v;
+  }
+  return kFilterMinPairs;
+}
 
 static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, void* base,
                        size_t cap, SearchWs* ws) {
@@ -238,7 +251,7 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
   ws->Kp = tensor ? coarse_candidates(k, N) : k;
   // filter strategy: capacity 4 K' (>= 4096), aiming at capacity / 4 survivors
   ws->cap = 4 * ws->Kp < 4096 ? 4096 : 4 * ws->Kp;
-  ws->filter = (tensor && N >= kFilterMinItems && (int64_t)ws->cap * 16 <= N) ? 1 : 0;
+  ws->filter = (tensor && N >= kFilterMinItems && (int64_t)ws->cap * 16 <= N && (int64_t)B * N >= filter_min_pairs()) ? 1 : 0;
   const int64_t n_rows = N > 0 ? N : 1;
   if (ws->filter) {
     const int64_t target = ws->cap / 4;

@@ -199,6 +199,59 @@ def search(
     return out_s, out_i
 
 
+class GraphedSearch:
+    """One mol_search call of a fixed signature (B, k, mode, user_ids or not) captured in a CUDA graph.
+
+    The C entry is stream-ordered, allocates nothing and never synchronises, so the ~25 launches of a search (query prologue,
+    coarse passes, selections, rescoring, the idle fallback launches) are captured once and replayed as one graph launch:
+    what is left of a small-batch search is kernel time.  Inputs are copied into the graph's static buffers; outputs are
+    returned as fresh tensors.  The graph owns its workspace (the shared grow-only Workspace may be reallocated by other
+    calls).  Build a new one when the weights or the index change."""
+
+    def __init__(self, weights: PackedWeights, index: IndexHandle, B: int, k: int, mode: int, has_uid: bool) -> None:
+        lib = _lib.load()
+        dev = index.device
+        self.weights, self.index, self.B, self.k, self.mode = weights, index, B, k, mode
+        self.q = torch.zeros((B, weights.shape.query_embedding_dim), dtype=torch.float32, device=dev)
+        self.uid = torch.zeros((B,), dtype=torch.int64, device=dev) if has_uid else None
+        self.out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+        self.out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+        nbytes = c_size_t()
+        _lib.check(lib.mol_search_workspace_bytes(byref(weights.shape), index.N, B, k, mode, byref(nbytes)))
+        self.workspace = Workspace(dev)
+        self.ws = self.workspace.get(nbytes.value)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside the capture (one-time function attributes, lazy module loading)
+            self._call()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._call()
+
+    def _call(self) -> None:
+        lib = _lib.load()
+        dev = self.index.device
+        with torch.cuda.device(dev):
+            _lib.check(
+                lib.mol_search(
+                    byref(self.weights.shape), byref(self.weights.struct), byref(self.index.struct), _ptr(self.q),
+                    _ptr(self.uid), self.B, self.k, 1, self.mode, _ptr(self.out_s), _ptr(self.out_i), _ptr(self.ws),
+                    self.ws.numel(), _stream_ptr(dev),
+                )
+            )
+
+    def __call__(self, queries: torch.Tensor, user_ids: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+        self.q.copy_(queries, non_blocking=True)
+        if self.uid is not None:
+            if user_ids is None:
+                raise KeyError("user_ids")
+            self.uid.copy_(user_ids, non_blocking=True)
+        self.graph.replay()
+        return self.out_s.clone(), self.out_i.clone()
+
+
 def search_stats(workspace: Workspace) -> Dict[str, int]:
     """Counters of the last search that used `workspace` (mol_search_stats; synchronises the stream)."""
     lib = _lib.load()

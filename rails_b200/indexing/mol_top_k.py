@@ -78,7 +78,11 @@ class MoLBruteForceTopK(MoLTopKModule):
         item_embeddings: torch.Tensor,
         item_ids: torch.Tensor,
         mode: int = _lib.MODE_AUTO,
+        cuda_graph: bool = False,
     ) -> None:
+        """mode / cuda_graph are extensions of the reference's constructor (mol_top_k.py:85-97).  cuda_graph=True replays
+        each (B, k) signature of forward() as one captured CUDA graph (engine.GraphedSearch): the launch overhead of the
+        ~25 kernels of a search disappears, which is most of the time of a small-batch call."""
         super().__init__(
             mol_module=mol_module,
             item_embeddings=item_embeddings,
@@ -87,6 +91,8 @@ class MoLBruteForceTopK(MoLTopKModule):
             keep_component_level_item_embeddings=False,
         )
         self._mode = mode
+        self._cuda_graph = bool(cuda_graph)
+        self._graphs = {}
         if item_embeddings.is_cuda:
             self._ensure_index()
 
@@ -111,9 +117,22 @@ class MoLBruteForceTopK(MoLTopKModule):
         """
         index = self._ensure_index()
         dev = index.device
+        weights = self._mol_module.packed_weights(dev)
+        if self._cuda_graph and query_embeddings.size(0) > 0:
+            uid = kwargs.get("user_ids")
+            key = (int(query_embeddings.size(0)), int(k), id(index), id(weights))
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) >= 8:  # (signatures of a serving loop are few; stale weights / indexes age out)
+                    self._graphs.pop(next(iter(self._graphs)))
+                g = engine.GraphedSearch(weights, index, key[0], key[1], self._mode, weights.shape.num_uid_tables > 0)
+                self._graphs[key] = g
+            engine._require_cuda(query_embeddings, "query_embeddings")
+            scores, ids = g(query_embeddings.detach().to(device=dev, dtype=torch.float32), uid)
+            return scores.to(query_embeddings.dtype), ids
         scores, ids = engine.search(
-            self._mol_module.packed_weights(dev), index, self._mol_module.workspace(dev), query_embeddings,
-            kwargs.get("user_ids"), int(k), sorted, self._mode,
+            weights, index, self._mol_module.workspace(dev), query_embeddings, kwargs.get("user_ids"), int(k), sorted,
+            self._mode,
         )
         return scores.to(query_embeddings.dtype), ids
 

@@ -23,8 +23,14 @@ def _stats(mol):
     return engine.search_stats(mol.workspace(torch.device(DEV)))
 
 
+@pytest.fixture
+def force_filter(monkeypatch):
+    """The fused-filter strategy is used from 2^24 (query, item) pairs; these tests reach it with a handful of queries."""
+    monkeypatch.setenv("MOL_B200_FILTER_MIN_PAIRS", "0")
+
+
 @pytest.mark.parametrize("mode", [_lib.MODE_AUTO, _lib.MODE_EXACT])
-def test_large_reference_fixture_filter_strategy(mode):
+def test_large_reference_fixture_filter_strategy(mode, force_filter):
     """150 000 items: above kFilterMinItems, so MODE_AUTO takes the strided-sample threshold + fused filter path.  The
     expected values are outputs of the UNMODIFIED reference (oracle/gen_golden_large.py)."""
     from tests.golden_util import load_large
@@ -51,7 +57,7 @@ def test_large_reference_fixture_filter_strategy(mode):
         assert (sc[:, :: g["col_stride"]].cpu() - g["ref_scores_strided"]).abs().max().item() <= 2e-4
 
 
-def test_north_star_16_queries_full_corpus_vs_oracle():
+def test_north_star_16_queries_full_corpus_vs_oracle(force_filter):
     """The benchmarked configuration (8x8x32, 1M items, top-100): 16 queries against the CPU oracle over the FULL corpus."""
     cfg = CFG_8x8x32
     N, B, k = 1_000_000, 16, 100
@@ -116,7 +122,7 @@ def test_acceptance_check_10k_queries_no_miss():
     assert miss == 0
 
 
-def test_dense_scores_tiny_gap_falls_back_and_stays_exact():
+def test_dense_scores_tiny_gap_falls_back_and_stays_exact(force_filter):
     """Adversarial for the acceptance test: the corpus is a few hundred prototypes, each repeated ~hundreds of times with
     perturbations far below the coarse pass's resolution, so the gap between rank k and rank K' is ~1e-5 while the coarse
     error is ~1e-2.  The check must refuse the coarse candidate set (flag the queries) and the exact fallback must return
@@ -172,7 +178,7 @@ def test_ordered_corpus_no_fallback_and_no_slowdown():
     assert ms1 <= 1.1 * ms0 + 0.05, (ms0, ms1)
 
 
-def test_prepared_weights_equal_per_call_preparation():
+def test_prepared_weights_equal_per_call_preparation(force_filter):
     """mol_weights_prepare (once per weight version) vs weights->prepared == NULL (operands recomputed inside every call)."""
     cfg = CFG_8x8x32
     N, B, k = 70_000, 9, 50
@@ -225,3 +231,47 @@ def test_bf16_model_and_inputs():
     assert (s.float().cpu() - rs).abs().max().item() <= 2.0 ** -7 * float(rs.abs().max()) + 1e-3
     sc, _ = mol(q, items.unsqueeze(0))
     assert sc.dtype == torch.bfloat16 and sc.shape == (B, N)
+
+
+def test_small_batches_take_the_matrix_strategy_and_agree_with_the_filter_strategy(monkeypatch):
+    """Below 2^24 (query, item) pairs the coarse pass writes its score matrix (one launch + one select) instead of running
+    the threshold pass; both strategies must return the same answer."""
+    cfg = CFG_8x8x32
+    N, B, k = 200_000, 4, 100
+    mol, _ = build_module(cfg, None, DEV, seed=5)
+    items, ids, q, _ = synthetic_inputs(cfg, N, B, 5, DEV)
+    top = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0))
+    a = top(q, k=k)
+    st_a = _stats(mol)
+    monkeypatch.setenv("MOL_B200_FILTER_MIN_PAIRS", "0")
+    b = top(q, k=k)
+    st_b = _stats(mol)
+    assert st_a["tensor_path"] == 1 and st_a["filter_strategy"] == 0 and st_b["filter_strategy"] == 1, (st_a, st_b)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+
+
+def test_cuda_graph_search_equals_eager():
+    """MoLBruteForceTopK(cuda_graph=True): every (B, k) signature is captured once and replayed; results are the eager ones,
+    replays with new queries see the new queries, and the real ML-1M configuration (uid embeddings) works through it."""
+    from tests.golden_util import load_golden
+
+    cfg = CFG_8x8x32
+    N, k = 50_000, 50
+    mol, _ = build_module(cfg, None, DEV, seed=6)
+    items, ids, q, _ = synthetic_inputs(cfg, N, 24, 6, DEV)
+    eager = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0))
+    graphed = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), cuda_graph=True)
+    for B in (1, 8, 8, 24, 1):
+        for off in (0, 3):
+            qq = q[off : off + B] if off + B <= 24 else q[:B]
+            es, ei = eager(qq, k=k)
+            gs, gi = graphed(qq, k=k)
+            assert torch.equal(ei, gi) and torch.equal(es, gs), (B, off)
+    g = load_golden("cfg1_ml1m_ckpt")
+    mol1, _ = build_module(g["cfg"], g["sd"], DEV)
+    top1 = MoLBruteForceTopK(mol1, g["items"].to(DEV).unsqueeze(0), g["item_ids"].to(DEV).unsqueeze(0), cuda_graph=True)
+    u = g["user_ids"].to(DEV)
+    for _ in range(2):
+        s, i = top1(g["queries"].to(DEV), k=g["k"], user_ids=u)
+        r = O.compare_top_k(s, i, g["ref_scores"], g["item_ids"], g["k"], SCORE_TOL, TIE_TOL)
+        assert r["ok"] == 1.0, r

@@ -281,8 +281,14 @@ def test_full_size_properties_1m_items():
     assert r["max_score_err"] <= SCORE_TOL, r
 
 
+@pytest.fixture
+def force_filter(monkeypatch):
+    """The fused-filter strategy is used from 2^24 (query, item) pairs; these tests reach it with a handful of queries."""
+    monkeypatch.setenv("MOL_B200_FILTER_MIN_PAIRS", "0")
+
+
 @pytest.mark.parametrize("order", ["descending", "ascending"])
-def test_filter_strategy_survives_adversarial_item_order(order):
+def test_filter_strategy_survives_adversarial_item_order(order, force_filter):
     """The fused candidate filter takes its per-query threshold from the first items of the corpus.  Sorting the
     corpus by one query's score makes that sample as unrepresentative as possible (threshold far too high /
     far too low): the safety check must notice and the exact fallback must still return the right answer."""
@@ -302,7 +308,7 @@ def test_filter_strategy_survives_adversarial_item_order(order):
 
 
 @pytest.mark.parametrize("N,B,k", [(400_003, 2, 2500), (262_144, 1, 1), (999_963, 3, 200)])
-def test_filter_strategy_edge_sizes_match_exact_mode(N, B, k):
+def test_filter_strategy_edge_sizes_match_exact_mode(N, B, k, force_filter):
     """Large k (capacity 4 K' > 4096), ragged last tile, single query, k = 1 on the fused-filter strategy: the tensor
     path must return exactly what the fp32 exact mode returns."""
     cfg = CFG_8x8x32
@@ -586,6 +592,7 @@ def _nccl_worker(rank, world, port, out):
     try:
         cfg = CFG_8x8x32
         N, B, k = 400_000, 16, 100
+        os.environ["MOL_B200_FILTER_MIN_PAIRS"] = "0"  # (16 queries: force the fused-filter strategy)
         mol, _ = build_module(cfg, None, dev, seed=2)
         items, ids, q, _ = synthetic_inputs(cfg, N, B, 2, dev)
         lo, hi = shard_range(N, rank, world)
@@ -594,9 +601,11 @@ def _nccl_worker(rank, world, port, out):
         full = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0))
         rs, ri = full(q, k)
         ok = bool(torch.equal(i, ri)) and bool(torch.equal(s, rs))
-        # query-split layout over the replicated corpus (ragged: 15 queries over 2 ranks)
+        # query-split layout over the replicated corpus (ragged: 15 queries over 2 ranks).  Slices of <= 8 queries take the
+        # small-batch prologue kernels, whose sums may differ from the 16-query batch in the last bit: ids equal, scores
+        # to 1e-5
         s2, i2 = ReplicatedMoLBruteForceTopK(full)(q[:15], k)
-        ok = ok and bool(torch.equal(i2, ri[:15])) and bool(torch.equal(s2, rs[:15]))
+        ok = ok and bool(torch.equal(i2, ri[:15])) and float((s2 - rs[:15]).abs().max()) < 1e-5
         # k beyond the corpus: RuntimeError on every rank, before any collective
         try:
             ShardedMoLBruteForceTopK(local, hi - lo)(q, N + 1)
