@@ -1079,6 +1079,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
 
 #include "mol_coarse_v3.cuh"
+#include "mol_coarse_l256.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Operand images
@@ -1162,7 +1163,9 @@ int coarse_gi_image(const mol_shape_t& s, const float* gi_f32, uint16_t* gi_half
 // ------------------------------------------------------------------------------------------------
 bool coarse_supported(const mol_shape_t& s) {
   Dims D = dims_of(s);
-  if (D.Pq != kPQ || D.H != kH) return false;
+  if (D.H != kH) return false;
+  if (D.Pq == 16 && D.Px == 16 && D.d == 64) return true;  // L = 256: mol_coarse256_kernel
+  if (D.Pq != kPQ) return false;
   if (D.Px == 8 && D.d == 32) return true;
   if (D.Px == 4 && (D.d == 64 || D.d == 128)) return true;
   return false;
@@ -1302,10 +1305,56 @@ static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const Coar
   return MOL_OK;
 }
 
+// L = 256 (16 x 16 x 64): everything of a (query, tile) unit is streamed, see mol_coarse_l256.cuh
+static int launch_coarse256(const mol_index_t& ix, const CoarseWs& ws, int bc, const CoarseOut& out, cudaStream_t st) {
+  using C = l256::Cfg256<16, 16, 64>;
+  const int64_t N = ix.num_items;
+  const int64_t Np = (N + kTile - 1) / kTile * kTile;
+  CUtensorMap tmX, tmGI;
+  MOL_TRY(encode_2d(&tmX, ix.xsub_half, 16 * 64, (uint64_t)Np, 64, kTile, CU_TENSOR_MAP_SWIZZLE_128B));
+  MOL_TRY(encode_2d(&tmGI, ix.gi_half, C::L, (uint64_t)Np, 64, kTile, CU_TENSOR_MAP_SWIZZLE_128B));
+  CoarseParams P;
+  P.trace = (long long*)coarse_trace_buffer();
+  P.w1_img = ws.w1_img;
+  P.w2_img = ws.w2_img;
+  P.q_rec = ws.q_rec;
+  P.scores = out.scores;
+  P.thr = out.thr;
+  P.thr_stride = out.thr_stride;
+  P.cand_cnt = out.cand_cnt;
+  P.cand_scores = out.cand_scores;
+  P.cand_idx = out.cand_idx;
+  P.cand_cap = out.cand_cap;
+  P.N = N;
+  P.ld = out.ld;
+  P.tile_begin = out.tile_begin;
+  P.tile_end = out.tile_end < 0 ? (int)(Np / kTile) : out.tile_end;
+  P.tile_map = out.tile_map;
+  P.bc = bc;
+  if (P.tile_end <= P.tile_begin) return MOL_OK;
+  static int sms = 0;
+  if (sms == 0) {
+    MOL_CUDA(cudaFuncSetAttribute(l256::mol_coarse256_kernel<16, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM_BYTES));
+    int dev = 0, n = 148;
+    MOL_CUDA(cudaGetDevice(&dev));
+    MOL_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    sms = n;
+  }
+  const int64_t F = (int64_t)(P.tile_end - P.tile_begin) * bc;
+  MOL_CHECK_ARG(F < (1ll << 31), "coarse pass: tiles x queries = %lld does not fit 32 bits (use smaller query chunks)", (long long)F);
+  int grid = (int)(F < sms ? F : sms);
+  if (grid < 1) grid = 1;
+  l256::mol_coarse256_kernel<16, 16, 64><<<grid, l256::kThreadsL, C::SMEM_BYTES, st>>>(tmX, tmGI, P);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
 int coarse_run(const mol_shape_t& s, const mol_index_t& ix, const CoarseWs& ws, int bc, const CoarseOut& out,
                cudaStream_t st) {
   Dims D = dims_of(s);
   if (bc == 0 || ix.num_items == 0) return MOL_OK;
+  if (D.Pq == 16 && D.Px == 16 && D.d == 64) return launch_coarse256(ix, ws, bc, out, st);
   if (D.Px == 8 && D.d == 32) return launch_coarse<8, 32>(s, ix, ws, bc, out, st);
   if (D.Px == 4 && D.d == 64) return launch_coarse<4, 64>(s, ix, ws, bc, out, st);
   if (D.Px == 4 && D.d == 128) return launch_coarse<4, 128>(s, ix, ws, bc, out, st);

@@ -8,11 +8,11 @@ sys.path.insert(0, ROOT)
 import torch
 
 from rails_b200 import engine
-from rails_b200.workloads import CFG_8x8x32, CFG_8x4x64, build_module, synthetic_inputs
+from rails_b200.workloads import CFG_8x8x32, CFG_8x4x64, CFG_16x16x64, build_module, synthetic_inputs
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 6
-cfg = CFG_8x4x64 if os.environ.get("DBG_CFG") == "8x4x64" else CFG_8x8x32
+cfg = {"8x4x64": CFG_8x4x64, "16x16x64": CFG_16x16x64}.get(os.environ.get("DBG_CFG", ""), CFG_8x8x32)
 dev = torch.device("cuda:0")
 mol, _ = build_module(cfg, None, dev, seed=3)
 items, ids, q, uid = synthetic_inputs(cfg, N, B, 3, dev)
