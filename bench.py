@@ -52,6 +52,7 @@ def parse():
     p.add_argument("--cpu-queries", type=int, default=32, help="queries in the cpu_baseline / parity sample (~11 s of CPU work)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-secondary", action="store_true", help="skip the secondary configs / batch sweep block")
+    p.add_argument("--no-cuda-graph", action="store_true", help="N > 1: launch each rank's search eagerly instead of as a CUDA graph")
     p.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-this-GPU baseline leg")
     return p.parse_args()
 
@@ -394,7 +395,9 @@ def main():
         if cfg.uid_embedding_hash_sizes:
             uid_dev = torch.randint(1, 100000, (B,), generator=gq, dtype=torch.int64).to(dev)
     q_dev = q_host.to(dev)
-    top = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=mode)
+    # N > 1: each rank's search is a few ms, so its ~30 launches are replayed as one CUDA graph (the public
+    # MoLBruteForceTopK(cuda_graph=True) option); the single-GPU legs below call the engine directly
+    top = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=mode, cuda_graph=(world > 1 and not args.no_cuda_graph))
     index = top._ensure_index()
     weights = mol.packed_weights(dev)
     wsp = mol.workspace(dev)
@@ -455,14 +458,16 @@ def main():
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
     value = B / (ms_step * 1e-3)
-    stats = engine.search_stats(wsp)  # counters of the last timed search on this rank
+    stats = engine.search_stats(wsp) if world == 1 else top.last_search_stats()  # counters of the last timed search on this rank
 
     # ---- the scoring kernel alone: a separate pass with the library's CUDA-event profiling switched on
     prof_steps = min(args.steps, 3)
+    graphed, top._cuda_graph = top._cuda_graph, False  # (a replayed graph does not pass through the library's event records)
     lib.mol_profile_enable(1)
     for _ in range(prof_steps):
         step_device()
     torch.cuda.synchronize()
+    top._cuda_graph = graphed
     k_ms, k_n = ctypes.c_double(), ctypes.c_int32()
     _lib.check(lib.mol_profile_collect(ctypes.byref(k_ms), ctypes.byref(k_n)))
     lib.mol_profile_enable(0)
@@ -567,6 +572,8 @@ def main():
     if rank == 0:
         par = {"single": "single GPU", "replicate": f"corpus replicated, queries split x{world}, one all-gather",
                "shard": f"corpus sharded x{world}, one all-gather + merge"}[layout]
+        if world > 1 and not args.no_cuda_graph:
+            par += "; per-rank search replayed as a CUDA graph"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",

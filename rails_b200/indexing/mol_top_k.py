@@ -96,6 +96,13 @@ class MoLBruteForceTopK(MoLTopKModule):
         if item_embeddings.is_cuda:
             self._ensure_index()
 
+    def last_search_stats(self) -> dict:
+        """Counters of the last forward() (engine.search_stats: exact-fallback queries, filter overflows, ...)."""
+        ws = getattr(self, "_last_workspace", None)
+        if ws is None:
+            raise RuntimeError("forward() has not been called yet")
+        return engine.search_stats(ws)
+
     @torch.no_grad()
     def forward(
         self,
@@ -129,7 +136,9 @@ class MoLBruteForceTopK(MoLTopKModule):
                 self._graphs[key] = g
             engine._require_cuda(query_embeddings, "query_embeddings")
             scores, ids = g(query_embeddings.detach().to(device=dev, dtype=torch.float32), uid)
+            self._last_workspace = g.workspace
             return scores.to(query_embeddings.dtype), ids
+        self._last_workspace = self._mol_module.workspace(dev)
         scores, ids = engine.search(
             weights, index, self._mol_module.workspace(dev), query_embeddings, kwargs.get("user_ids"), int(k), sorted,
             self._mode,
