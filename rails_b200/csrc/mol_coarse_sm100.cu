@@ -69,33 +69,6 @@ static_assert(256 * kE13Regs + 256 * kE2Regs + 128 * kCtlRegs <= kThreads * 96, 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kK3 = kH + 16;    // K of the gate GEMM's TS part: hidden units + the ones block
 constexpr int kSmemLimit = 232448;
-constexpr float kGateClamp = 40.f;  // clamp of the half gate pre-activation u (silu(2u) <= 80 -> e^w finite in fp32)
-#ifndef MOL_EX2_EMU_OF4
-#define MOL_EX2_EMU_OF4 0  // measured on B200: 0 is fastest ("what did not work")
-#endif
-constexpr int kEx2EmuOf4 = MOL_EX2_EMU_OF4;
-#ifndef MOL_G1_SPLIT
-#define MOL_G1_SPLIT 0  // measured: 35.5 ms split vs 34.4 ms unsplit per 512 x 1M step
-#endif
-constexpr bool kG1Split = MOL_G1_SPLIT != 0;
-#ifndef MOL_G1_LATE
-#define MOL_G1_LATE 0  // not yet measured
-#endif
-// the next query's G1 (790 clk of tensor pipe, result not needed before this query's E2 ends) is issued behind G3's first
-// part instead of directly behind G2, so it does not sit in front of the other slot's latency-critical G2 / G3
-constexpr bool kG1Late = MOL_G1_LATE != 0;
-#ifndef MOL_E1_EARLY
-#define MOL_E1_EARLY 0  // measured: 35.6 ms early vs 34.6 ms at the loop top per 512 x 1M step
-#endif
-constexpr bool kE1Early = MOL_E1_EARLY != 0;
-#ifndef MOL_G1_PAIR
-#define MOL_G1_PAIR 0
-#endif
-// slot 0's issuer issues the G1 MMAs of BOTH slots back to back per item-tile slice (collector::a::fill -> ::lastuse, the
-// second MMA skips the 4 KB shared-memory fetch of A: 26.6 instead of 39.9 clk per MMA)
-constexpr bool kG1Pair = MOL_G1_PAIR != 0;
-static_assert(!(kG1Pair && kG1Split), "MOL_G1_PAIR and MOL_G1_SPLIT are exclusive");
-static_assert(!(kG1Late && (kG1Split || kG1Pair)), "MOL_G1_LATE excludes MOL_G1_SPLIT / MOL_G1_PAIR");
 #ifndef MOL_E2_POLY_MASK
 #define MOL_E2_POLY_MASK 0  // (round 1 shipped 0x0E; the half2 form below measured 5.5 % faster)
 #endif
@@ -113,27 +86,12 @@ constexpr unsigned long long expand_chunk_mask(unsigned m) {
 }
 constexpr unsigned long long kE2Poly64 = expand_chunk_mask(kE2PolyMask);
 #endif
-#ifndef MOL_E3_POLY_OF4
-#define MOL_E3_POLY_OF4 0
-#endif
-// of every 4 logit pairs of E3, how many take tanh from the polynomial instead of MUFU.TANH
-constexpr int kE3PolyOf4 = MOL_E3_POLY_OF4;
-// tanh(u) ~ c * Q(c^2), c = clamp(u, +-kTanhC) (weighted least-squares minimax fits, fp32 Horner):
-//   MOL_E2_POLY_DEG 6: clamp 3.5,  |error| <= 1.9e-3;   8: clamp 3.75, |error| <= 6.3e-4 (MUFU.TANH.F16 itself: ~5e-4)
-#ifndef MOL_E2_POLY_DEG
-#define MOL_E2_POLY_DEG 8
-#endif
-#if MOL_E2_POLY_DEG == 6
-constexpr float kTanhC = 3.5f;
-constexpr float kT0 = 0.9905173778533936f, kT1 = -0.29184621572494507f, kT2 = 0.07649415731430054f,
-                kT3 = -0.013051184825599194f, kT4 = 0.0013143233954906464f, kT5 = -7.031815766822547e-05f,
-                kT6 = 1.5339735455199843e-06f, kT7 = 0.f, kT8 = 0.f;
-#else
+// tanh(u) ~ c * Q(c^2), c = clamp(u, +-3.75) (weighted least-squares minimax fit, fp32 Horner): |error| <= 6.3e-4
+// (MUFU.TANH.F16 itself: ~5e-4)
 constexpr float kTanhC = 3.75f;
 constexpr float kT0 = 0.996860146522522f, kT1 = -0.3149697482585907f, kT2 = 0.10022653639316559f,
                 kT3 = -0.023737963289022446f, kT4 = 0.003820218378677964f, kT5 = -0.0003979474422521889f,
                 kT6 = 2.547265285102185e-05f, kT7 = -9.067708219845372e-07f, kT8 = 1.3707315282829313e-08f;
-#endif
 
 // ---- MUFU-free silu(2u) in packed half2 (design + constants: tools/fit_silu_h2.py; not yet measured on the GPU) ------
 //   silu(2u) = (u + |u|) - s(|u|),   s(a) = a (1 - tanh a) in [0, 0.28]  ~  a * w * Q(w),   w = relu(1 - a/A)^4
@@ -145,25 +103,11 @@ constexpr float kT0 = 0.996860146522522f, kT1 = -0.3149697482585907f, kT2 = 0.10
 #endif
 // bit c set: chunk c (16 hidden units) of E2 uses the half2 form (takes precedence over MOL_E2_POLY_MASK for that chunk)
 constexpr unsigned kE2H2Mask = MOL_E2_H2_MASK;
-#ifndef MOL_E3_H2_OF4
-#define MOL_E3_H2_OF4 0
-#endif
-// of every 4 logit pairs of E3, how many take s(|u|) from the half2 form (the large part u + |u| stays in fp32)
-constexpr int kE3H2Of4 = MOL_E3_H2_OF4;
-#ifndef MOL_H2_LITE
-#define MOL_H2_LITE 0
-#endif
 constexpr uint32_t h2x2(unsigned bits16) { return (uint32_t)bits16 * 0x00010001u; }
 constexpr uint32_t kH2One = h2x2(0x3C00);
-#if MOL_H2_LITE
-// A = 5.5, Q of degree 1: 8 instructions, max |error| 7.4e-3, rms 2.7e-3
-constexpr uint32_t kH2NegInvA = h2x2(0xB1D1);
-constexpr uint32_t kH2NC0 = h2x2(0xABCE), kH2NC1 = h2x2(0xBC2C), kH2NC2 = 0u, kH2NC3 = 0u;
-#else
 // A = 6, Q of degree 3 (negated coefficients: -0.05252, -0.35986, -1.68262, +1.09277)
 constexpr uint32_t kH2NegInvA = h2x2(0xB155);
 constexpr uint32_t kH2NC0 = h2x2(0xAAB9), kH2NC1 = h2x2(0xB5C2), kH2NC2 = h2x2(0xBEBB), kH2NC3 = h2x2(0x3C5F);
-#endif
 // a = |u|, aw = a * w, nq = -Q(w)   ->   -s(|u|) = aw * nq
 __device__ __forceinline__ void h2_bump_parts(uint32_t u2, uint32_t& a, uint32_t& aw, uint32_t& nq) {
   a = u2 & 0x7fff7fffu;
@@ -171,13 +115,9 @@ __device__ __forceinline__ void h2_bump_parts(uint32_t u2, uint32_t& a, uint32_t
   y = mul_f16x2(y, y);
   const uint32_t w = mul_f16x2(y, y);
   aw = mul_f16x2(a, w);
-#if MOL_H2_LITE
-  nq = fma_f16x2(kH2NC1, w, kH2NC0);
-#else
   nq = fma_f16x2(kH2NC3, w, kH2NC2);
   nq = fma_f16x2(nq, w, kH2NC1);
   nq = fma_f16x2(nq, w, kH2NC0);
-#endif
 }
 // silu(2u) for two packed fp16 values
 __device__ __forceinline__ uint32_t silu2_h2(uint32_t u2) {
@@ -185,22 +125,6 @@ __device__ __forceinline__ uint32_t silu2_h2(uint32_t u2) {
   h2_bump_parts(u2, a, aw, nq);
   return fma_f16x2(aw, nq, add_f16x2(u2, a));
 }
-// -s(|u|) for two packed fp16 values
-__device__ __forceinline__ uint32_t neg_bump_h2(uint32_t u2) {
-  uint32_t a, aw, nq;
-  h2_bump_parts(u2, a, aw, nq);
-  return mul_f16x2(aw, nq);
-}
-
-#ifndef MOL_E2_SHARE
-#define MOL_E2_SHARE 0
-#endif
-// the last MOL_E2_SHARE (0, 1 or 2) 16-unit chunks of E2 are converted by the slot's E3 warpgroup, after its E3 of the
-// previous query (that group idles ~0.8k clk per query waiting for the E1/E2 group, which is the longer chain:
-// profiles/r01_trace_slot0.log).  e2_done then collects both groups.  Not yet measured on the GPU.
-constexpr int kE2Share = MOL_E2_SHARE;
-static_assert(kE2Share >= 0 && kE2Share <= 2, "MOL_E2_SHARE must be 0, 1 or 2");
-
 // TMEM column map of one slot (256 columns)
 constexpr uint32_t kColLog = 0;     // LOG fp32 [0, L); A2 fp16 aliases [0, L/2) + ones [L/2, L/2 + 8)
 constexpr uint32_t kColHid = 64;    // HID fp32 [64, 192); A3 fp16 aliases [64, 128) + ones [128, 136)
@@ -271,9 +195,7 @@ struct Bars {
   uint64_t full[2], empty[2];
   uint64_t q0_ready[2], e1_done[2], a2_read[2], e2a_done[2], e2_done[2], gate_free[2];
   uint64_t log_full[2], hid_full[2], gate_full[2];
-  uint64_t g1_req;       // MOL_G1_PAIR: slot 1 is ready for its next G1 (arrived by its issuer, consumed by slot 0's)
   uint32_t tmem_base;
-  uint32_t issue_lock;   // MOL_G1_PAIR: held while a fill -> lastuse group is open / while slot 1's issuer issues
 };
 
 // Walks this CTA's flat range of (tile, query) units tile by tile.
@@ -338,13 +260,9 @@ __device__ __forceinline__ void e2_act_chunk(const uint32_t* v, uint32_t taddr, 
       const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
       const float2 c = make_float2(clamp_sym(u.x, kTanhC), clamp_sym(u.y, kTanhC));
       const float2 s2 = __fmul2_rn(c, c);
-#if MOL_E2_POLY_DEG == 6
-      float2 p = __ffma2_rn(make_float2(kT6, kT6), s2, make_float2(kT5, kT5));
-#else
       float2 p = __ffma2_rn(make_float2(kT8, kT8), s2, make_float2(kT7, kT7));
       p = __ffma2_rn(p, s2, make_float2(kT6, kT6));
       p = __ffma2_rn(p, s2, make_float2(kT5, kT5));
-#endif
       p = __ffma2_rn(p, s2, make_float2(kT4, kT4));
       p = __ffma2_rn(p, s2, make_float2(kT3, kT3));
       p = __ffma2_rn(p, s2, make_float2(kT2, kT2));
@@ -405,14 +323,12 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_init(&bars->e1_done[s], 128);
       mbar_init(&bars->a2_read[s], 128);
       mbar_init(&bars->e2a_done[s], 128);
-      mbar_init(&bars->e2_done[s], kE2Share > 0 ? 256 : 128);
+      mbar_init(&bars->e2_done[s], 128);
       mbar_init(&bars->gate_free[s], 128);
       mbar_init(&bars->log_full[s], 1);
       mbar_init(&bars->hid_full[s], 1);
       mbar_init(&bars->gate_full[s], 1);
     }
-    mbar_init(&bars->g1_req, 1);
-    bars->issue_lock = 0u;
     fence_mbar_init();
   }
   if (warp == kCtlWarp0) tmem_alloc<512>(&bars->tmem_base);
@@ -467,16 +383,12 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       uint32_t c1 = 0, c2 = 0;  // completed e1_done / e2_done phases of this slot
       bool first = true, pre_g1 = false;
 
-      // part 2: the whole G1 + commit; part 0: the first half of the item-group MMAs; part 1: the second half + commit.
-      // Split in two, the next query's (not yet urgent) G1 never holds the in-order tensor pipe for more than half its
-      // length in front of the other slot's G2 / G3, whose epilogue warps are waiting (MOL_G1_SPLIT).
-      auto issue_g1 = [&](int s, int part) __attribute__((always_inline)) {
+      // G1 of one query from the item tile in stage s, then the commit that announces LOG
+      auto issue_g1 = [&](int s) __attribute__((always_inline)) {
         const uint32_t sXa = smem_u32(sX + s * C::X_BYTES);
-        const int gb = part == 1 ? C::NG / 2 : 0, ge = part == 0 ? C::NG / 2 : C::NG;
         if (elect_one_sync()) {
 #pragma unroll
           for (int g = 0; g < C::NG; ++g) {
-            if (g < gb || g >= ge) continue;
 #pragma unroll
 #ifdef MOL_ABLATE_G1
             for (int ks = 0; ks < C::K1 / 32; ++ks) {  // (timing experiment: half the K steps)
@@ -489,62 +401,10 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               umma_ss(base + kColLog + g * 16, da, db, idesc1, ks > 0);
             }
           }
-          if (part != 0) umma_commit(&bars->log_full[wg]);
+          umma_commit(&bars->log_full[wg]);
         }
         __syncwarp();
       };
-
-      // ---- MOL_G1_PAIR ------------------------------------------------------------------------------------------
-      // Both slots walk the same tiles; inside a tile slot 0 holds the queries qa, qa+2, ... and slot 1 qa+1, qa+3, ...,
-      // so the p-th query of slot 0 and the p-th of slot 1 read the same item tile: their G1s are issued as one
-      // sequence by slot 0's issuer.  Slot 1's issuer announces "LOG free + image staged" on g1_req at the points where
-      // it would have issued its own G1, and takes issue_lock around its other MMA groups, because an MMA landing
-      // between a collector fill and its lastuse would replace the buffered A slice.
-      uint32_t pc = 0;  // paired G1s issued so far (slot 0) -> phase of g1_req
-      auto lock_issue = [&]() __attribute__((always_inline)) {  // (elected lane only)
-        while (atomicCAS(&bars->issue_lock, 0u, 1u) != 0u) __nanosleep(32);
-      };
-      auto unlock_issue = [&]() __attribute__((always_inline)) { atomicExch(&bars->issue_lock, 0u); };
-      auto issue_g1_pair = [&](int s) __attribute__((always_inline)) {
-        const uint32_t sXa = smem_u32(sX + s * C::X_BYTES);
-        const uint32_t sQ0 = smem_u32(sQ), sQ1 = smem_u32(sQ + C::Q_BYTES);
-        if (elect_one_sync()) {
-          lock_issue();
-#pragma unroll
-          for (int g = 0; g < C::NG; ++g) {
-#pragma unroll
-            for (int ks = 0; ks < C::K1 / 16; ++ks) {
-              const int e = g * C::K1 + ks * 16;
-              const uint64_t da = make_smem_desc(sXa + (e / 64) * 16384 + (e % 64) * 2, 16, 1024, 2);
-              const uint64_t db0 = make_smem_desc(sQ0 + ks * 256, 128, (C::K1 / 8) * 128, 0);
-              const uint64_t db1 = make_smem_desc(sQ1 + ks * 256, 128, (C::K1 / 8) * 128, 0);
-              umma_ss_coll<1>(tmem + kColLog + g * 16, da, db0, idesc1, ks > 0);
-              umma_ss_coll<3>(tmem + 256u + kColLog + g * 16, da, db1, idesc1, ks > 0);
-            }
-          }
-          umma_commit(&bars->log_full[0]);
-          umma_commit(&bars->log_full[1]);
-          unlock_issue();
-        }
-        __syncwarp();
-      };
-      // the G1 of this slot's query number `p` (within its tile, whose slot-1 query count is n1) from stage `s`
-      auto do_g1 = [&](int s, int p, int n1, int part) __attribute__((always_inline)) {
-        if (!kG1Pair) {
-          issue_g1(s, part);
-        } else if (wg == 1) {
-          if (lane == 0) mbar_arrive(&bars->g1_req);
-          __syncwarp();
-        } else if (p < n1) {
-          mbar_wait_sleep(&bars->g1_req, pc & 1u);
-          ++pc;
-          tc_fence_after();
-          issue_g1_pair(s);
-        } else {
-          issue_g1(s, 2);  // odd query count in this tile: slot 0's last query has no partner
-        }
-      };
-      const bool locked = kG1Pair && wg == 1;  // slot 1's issuer serialises its MMA groups against open pairs
 
       TileWalk w(f0, f1, P.bc);
       int it = 0;
@@ -566,7 +426,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               mbar_wait_sleep(&bars->q0_ready[wg], 0);
               tc_fence_after();
             }
-            do_g1(s, 0, w.n_mine(1), 2);
+            issue_g1(s);
           }
           first = false;
           pre_g1 = false;
@@ -580,14 +440,12 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             ++c1;
             tc_fence_after();
             if (elect_one_sync()) {
-              if (locked) lock_issue();
 #pragma unroll
               for (int ks = 0; ks < C::K2 / 16; ++ks) {
                 const uint64_t db = make_smem_desc(sW1a + ks * 256, 128, (C::K2 / 8) * 128, 0);
                 umma_ts(base + kColHid, base + kColLog + ks * 8, db, idesc2, ks > 0);
               }
               umma_commit(&bars->hid_full[wg]);
-              if (locked) unlock_issue();
             }
             __syncwarp();
             // the next G1 overwrites LOG / A2 and reads the next query image: the E3 group must have copied the fp16
@@ -603,7 +461,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               g1_stage = sn;
               pre_g1 = true;
             }
-            if (g1_stage >= 0 && !kG1Late) do_g1(g1_stage, g1_stage == s && j + 1 < n ? j + 1 : 0, j + 1 < n ? w.n_mine(1) : wn.n_mine(1), kG1Split ? 0 : 2);
+            if (g1_stage >= 0) issue_g1(g1_stage);
             if (wg == 0) TR(2, 2, c2);
             // ---- G3, first part: needs the first half of A3 (E2), the diag of this query staged and GATE released
             //      by E3 of the previous query (gate_free; its first phase is arrived by the E1/E3 group's prologue)
@@ -612,7 +470,6 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             tc_fence_after();
             if (wg == 0) TR(2, 3, c2);
             if (elect_one_sync()) {
-              if (locked) lock_issue();
 #pragma unroll
 #ifdef MOL_ABLATE_DIAG
               for (int ks = 0; ks < 1; ++ks) {  // (timing experiment: one SS k-step only)
@@ -629,11 +486,8 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
                 umma_ts(base + kColGate, base + kColHid + ks * 8, db, idesc3, 1u);
               }
-              if (locked) unlock_issue();
             }
             __syncwarp();
-            if (kG1Split && g1_stage >= 0) issue_g1(g1_stage, 1);
-            if (kG1Late && g1_stage >= 0) issue_g1(g1_stage, 2);
             if (wg == 0) TR(2, 4, c2);
             // ---- G3, second part, once E2 has written all of A3
             mbar_wait_sleep(&bars->e2_done[wg], c2 & 1u);
@@ -641,7 +495,6 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             ++c2;
             tc_fence_after();
             if (elect_one_sync()) {
-              if (locked) lock_issue();
 #pragma unroll
               for (int ks = 4; ks < kK3 / 16; ++ks) {  // += [A3[:, 64:128] | 1] . [0.5 W2[:, 64:128] | 0.5 b2]^T
                 const uint64_t db = make_smem_desc(sW2a + ks * 256, 128, (kK3 / 8) * 128, 0);
@@ -649,7 +502,6 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               }
               umma_commit(&bars->gate_full[wg]);
               if (j == n - 1) umma_commit(&bars->empty[s]);  // every MMA of this slot that reads stage s is issued
-              if (locked) unlock_issue();
             }
             __syncwarp();
             if (wg == 0) TR(2, 6, c2 - 1);
@@ -674,9 +526,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     SlotSeq seq(f0, f1, P.bc, wg);
     int tile = 0, q = 0;
     uint32_t cnt = 0;
-    // E1 of the slot's k-th query.  It runs BETWEEN the two halves of E2 of the previous query (MOL_E1_EARLY): its
-    // log_full has long fired by then, and with e1_done already set the issuer queues G2 of the next query directly
-    // behind G3 of this one, instead of after a round trip through this warpgroup.
+    // E1 of the slot's k-th query
     auto do_e1 = [&](uint32_t k) __attribute__((always_inline)) {
       if (warp == 4) TR(1, 4, k);
       mbar_wait_sleep(&bars->log_full[wg], k & 1u);
@@ -714,14 +564,9 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (warp == 4) TR(1, 0, k);
     };
     bool have = seq.next(tile, q);
-    bool e1_pending = have;  // E1 of query `cnt` still to do at the top of the loop
     while (have) {
-      const int tile_cur = tile;
       const bool have_next = seq.next(tile, q);
-      // the next query's G1 is issued before this query's G3 only inside a tile, or across tiles when the next item
-      // tile has its own shared-memory stage; otherwise it waits for e2_done of this query and E1 must not block it
-      const bool e1_early = kE1Early && have_next && (C::STAGES > 1 || tile == tile_cur);
-      if (e1_pending) do_e1(cnt);
+      do_e1(cnt);
       // ---------------- E2
       mbar_wait_sleep(&bars->hid_full[wg], cnt & 1u);
       tc_fence_after();
@@ -732,9 +577,8 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       };
       // 8 chunks of 16 hidden units, loads one chunk ahead; A3 chunk c (8 columns) overwrites HID columns that
       // chunk c/2 (already in registers) came from
-      constexpr int nE2 = 8 - kE2Share;  // chunks [nE2, 8) are converted by the slot's E3 warpgroup (MOL_E2_SHARE)
       if constexpr (kHidF16) {
-        static_assert(!kHidF16 || (kE2Poly64 == 0 && kE2Share == 0), "MOL_HID_F16 supports the MUFU / half2 chunk forms only");
+        static_assert(!kHidF16 || kE2Poly64 == 0, "MOL_HID_F16 supports the MUFU / half2 chunk forms only");
         // packed loads, two chunks ahead (8 registers per chunk)
         uint32_t p0[8], p1[8], p2[8];
         tmem_ld_x8_pack16(base + kColHid, p0);
@@ -753,28 +597,23 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
         }
       } else {
-      tmem_ld_x16(base + kColHid, va);
+        tmem_ld_x16(base + kColHid, va);
 #pragma unroll
-      for (int c = 0; c < 8; c += 2) {
-        if (c < nE2) {
+        for (int c = 0; c < 8; c += 2) {
           tmem_ld_wait_bind16(va);
-          if (c + 1 < nE2) tmem_ld_x16(base + kColHid + 16 * (c + 1), vb);
+          tmem_ld_x16(base + kColHid + 16 * (c + 1), vb);
           act(va, kColHid + 8 * c, (unsigned)((kE2Poly64 >> (8 * c)) & 0xffull), ((kE2H2Mask >> c) & 1u) != 0);
-          if (c + 1 < nE2) {
-            tmem_ld_wait_bind16(vb);
-            if (c + 2 < nE2) tmem_ld_x16(base + kColHid + 16 * (c + 2), va);
-            act(vb, kColHid + 8 * (c + 1), (unsigned)((kE2Poly64 >> (8 * (c + 1))) & 0xffull),
-                ((kE2H2Mask >> (c + 1)) & 1u) != 0);
+          tmem_ld_wait_bind16(vb);
+          if (c + 2 < 8) tmem_ld_x16(base + kColHid + 16 * (c + 2), va);
+          act(vb, kColHid + 8 * (c + 1), (unsigned)((kE2Poly64 >> (8 * (c + 1))) & 0xffull),
+              ((kE2H2Mask >> (c + 1)) & 1u) != 0);
+          if (c == 2) {  // first half of A3 (k < 64) is in TMEM: the issuer may start G3
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars->e2a_done[wg]);
+            if (warp == 4) TR(1, 2, cnt);
           }
         }
-        if (c == 2) {  // first half of A3 (k < 64) is in TMEM: the issuer may start G3
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&bars->e2a_done[wg]);
-          if (warp == 4) TR(1, 2, cnt);
-          if (e1_early) do_e1(cnt + 1);  // (va, prefetched for chunk 4, stays live across it)
-        }
-      }
       }
       tmem_st_x8(base + kColHid + 64, ones);
       tmem_st_wait();
@@ -783,7 +622,6 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (warp == 4) TR(1, 3, cnt);
       ++cnt;
       have = have_next;
-      e1_pending = have_next && !e1_early;
     }
   } else if (warp < kCtlWarp0) {
     // =============================== E3 warpgroup of slot `wg` (+ query staging) ===============================
@@ -835,12 +673,6 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
     for (int i = 1; i < 8; ++i) ones[i] = 0u;
     const float2 l2e2 = make_float2(kLog2e, kLog2e);
-    const float2 magic2 = make_float2(12582912.f, 12582912.f), nmagic2 = make_float2(-12582912.f, -12582912.f);
-    const float2 neg1 = make_float2(-1.f, -1.f);
-    const float2 ec0 = make_float2(0.9999280571937561f, 0.9999280571937561f);
-    const float2 ec1 = make_float2(0.6932609677314758f, 0.6932609677314758f);
-    const float2 ec2 = make_float2(0.2426111251115799f, 0.2426111251115799f);
-    const float2 ec3 = make_float2(0.0551716685295105f, 0.0551716685295105f);
 
     // Stage order of this group: E1(j) -> E3(j-1).  E2(j) runs concurrently in the slot's other warpgroup, the MMAs
     // behind both.  The logits of two queries are live at once, as packed fp16 pairs (pkA / pkB alternate).
@@ -894,60 +726,15 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       auto gate = [&](const uint32_t* v, const uint32_t* lgc) __attribute__((always_inline)) {
 #pragma unroll
         for (int j2 = 0; j2 < 8; ++j2) {
-          float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
-          if (kEx2EmuOf4 > 0) {  // the exponent-field trick has no inf: keep e^w finite (w = silu(2u) <= 80)
-            u.x = fminf(u.x, kGateClamp);
-            u.y = fminf(u.y, kGateClamp);
-          }
+          const float2 u = make_float2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
           const float2 a = __fmul2_rn(u, l2e2);
-          float2 x;  // w * log2(e), w = silu(2u), in [-0.41, 116]
-          if ((j2 & 3) >= 4 - kE3H2Of4) {
-            // MUFU-free: w = (u + |u|) - s(|u|); the small bump s in packed half2, the large part in fp32
-            const uint32_t ns2 = neg_bump_h2(pack_f16x2(u.x, u.y));
-            const float2 ns = __half22float2(*reinterpret_cast<const __half2*>(&ns2));
-            x = __ffma2_rn(ns, l2e2, make_float2(a.x + fabsf(a.x), a.y + fabsf(a.y)));
-          } else {
 #ifdef MOL_ABLATE_E3
-          const float2 t = u;
+          const float2 e = __ffma2_rn(a, u, a);
 #else
-          float2 t;
-          if ((j2 & 3) >= 4 - kE3PolyOf4) {  // tanh of this logit pair on the FMA pipe (same polynomial as E2)
-            const float2 c = make_float2(clamp_sym(u.x, kTanhC), clamp_sym(u.y, kTanhC));
-            const float2 s2 = __fmul2_rn(c, c);
-            float2 p = __ffma2_rn(make_float2(kT8, kT8), s2, make_float2(kT7, kT7));
-            p = __ffma2_rn(p, s2, make_float2(kT6, kT6));
-            p = __ffma2_rn(p, s2, make_float2(kT5, kT5));
-            p = __ffma2_rn(p, s2, make_float2(kT4, kT4));
-            p = __ffma2_rn(p, s2, make_float2(kT3, kT3));
-            p = __ffma2_rn(p, s2, make_float2(kT2, kT2));
-            p = __ffma2_rn(p, s2, make_float2(kT1, kT1));
-            p = __ffma2_rn(p, s2, make_float2(kT0, kT0));
-            t = __fmul2_rn(c, p);
-          } else {
-            t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
-          }
+          const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+          const float2 x = __ffma2_rn(a, t, a);  // w * log2(e), w = silu(2u), in [-0.41, ...)
+          const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
 #endif
-          x = __ffma2_rn(a, t, a);
-          }
-          float2 e;
-          if ((j2 & 3) < kEx2EmuOf4) {
-            // 2^x on the FMA pipe: x = n + f, n = round(x) through the 1.5*2^23 trick, 2^f by a cubic (7.5e-5 rel.),
-            // 2^n by adding n to the exponent field (low mantissa bits of m hold n)
-            const float2 m = __fadd2_rn(x, magic2);
-            const float2 n = __fadd2_rn(m, nmagic2);
-            const float2 f = __ffma2_rn(n, neg1, x);
-            float2 pl = __ffma2_rn(ec3, f, ec2);
-            pl = __ffma2_rn(pl, f, ec1);
-            pl = __ffma2_rn(pl, f, ec0);
-            e.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(m.x) << 23));
-            e.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(m.y) << 23));
-          } else {
-#ifdef MOL_ABLATE_E3
-            e = x;
-#else
-            e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-#endif
-          }
           den[j2 & 3] = __fadd2_rn(den[j2 & 3], e);
           num[j2 & 3] = __ffma2_rn(e, __half22float2(*reinterpret_cast<const __half2*>(&lgc[j2])), num[j2 & 3]);
         }
@@ -1005,29 +792,6 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     };
 
-    // MOL_E2_SHARE: the last kE2Share chunks of E2 of the slot's current query (E1 index `cnt`), converted by this group.
-    // Their A3 columns alias the fp32 HID columns of chunk 3, which the E1/E2 group has loaded once e2a_done fires.
-    // (hid_full / e2a_done cannot run a phase ahead of this wait: G2 of the next query is issued behind e2_done of this
-    // one, which needs this group's arrival.)
-    auto e2_share = [&]() __attribute__((always_inline)) {
-      if constexpr (kE2Share > 0) {
-        mbar_wait_sleep(&bars->hid_full[wg], cnt & 1u);
-        mbar_wait_sleep(&bars->e2a_done[wg], cnt & 1u);
-        tc_fence_after();
-        uint32_t hv[16];
-#pragma unroll
-        for (int c = 8 - kE2Share; c < 8; ++c) {
-          tmem_ld_x16(base + kColHid + 16 * c, hv);
-          tmem_ld_wait_bind16(hv);
-          e2_act_chunk(hv, base + kColHid + 8 * c, (unsigned)((kE2Poly64 >> (8 * c)) & 0xffull),
-                       ((kE2H2Mask >> c) & 1u) != 0);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bars->e2_done[wg]);
-      }
-    };
-
     uint32_t pkA[L / 2], pkB[L / 2];
     int tile_p = 0, q_p = 0;
     bool have_p = false;
@@ -1046,7 +810,6 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       } else if (have_nn) {
         load_image(q_nn);
       }
-      e2_share();  // (no-op unless MOL_E2_SHARE)
       ++cnt;
       tile_p = tile;
       q_p = q;
@@ -1239,9 +1002,7 @@ static void* g_trace = nullptr;
 #define MOL_STR2(x) #x
 #define MOL_STR(x) MOL_STR2(x)
 const char* coarse_build_knobs() {
-  return "e2poly=" MOL_STR(MOL_E2_POLY_MASK) " e2h2=" MOL_STR(MOL_E2_H2_MASK) " e3poly=" MOL_STR(MOL_E3_POLY_OF4)
-         " e3h2=" MOL_STR(MOL_E3_H2_OF4) " h2lite=" MOL_STR(MOL_H2_LITE) " ex2emu=" MOL_STR(MOL_EX2_EMU_OF4)
-         " e2share=" MOL_STR(MOL_E2_SHARE) " g1late=" MOL_STR(MOL_G1_LATE) " hidf16=" MOL_STR(MOL_HID_F16);
+  return "e2poly=" MOL_STR(MOL_E2_POLY_MASK) " e2h2=" MOL_STR(MOL_E2_H2_MASK) " hidf16=" MOL_STR(MOL_HID_F16);
 }
 
 void* coarse_trace_buffer() { return g_trace; }

@@ -1,4 +1,4 @@
-"""CPU checks of the MUFU-free half2 silu(2u) that the coarse kernel can be built with (MOL_E2_H2_MASK / MOL_E3_H2_OF4):
+"""CPU checks of the MUFU-free half2 silu(2u) that the coarse kernel can be built with (MOL_E2_H2_MASK):
 the fp16 constants in the CUDA source are the ones the numerics model uses, and the emulated instruction sequence is as
 accurate as the shipped MUFU.TANH.F16 path (tools/fit_silu_h2.py is the design script)."""
 import os
@@ -24,11 +24,11 @@ def _f16_of_bits(bits: int) -> float:
 
 
 def _source_constants():
-    """{lite: (inv_a, (nc0, nc1, ...))} parsed from the kH2* definitions of the kernel source."""
-    src = open(SRC).read()
-    lite_block, main_block = re.search(r"#if MOL_H2_LITE\n(.*?)#else\n(.*?)#endif", src, re.S).groups()
+    """{lite: (inv_a, (nc0, nc1, ...))} parsed from the kH2* definitions of the kernel source (the degree-1 "lite" form
+    was measured in round 1 and removed from the kernel; it only lives on in the numerics model)."""
+    block = open(SRC).read()
     out = {}
-    for lite, block in ((True, lite_block), (False, main_block)):
+    for lite in (False,):
         inv_a = _f16_of_bits(int(re.search(r"kH2NegInvA = h2x2\((0x[0-9A-Fa-f]+)\)", block).group(1), 16))
         nc = [
             _f16_of_bits(int(m, 16))
@@ -40,7 +40,7 @@ def _source_constants():
 
 def test_kernel_constants_equal_the_model_constants():
     src = _source_constants()
-    for lite in (False, True):
+    for lite in (False,):
         inv_a, nc = src[lite]
         k = sim_coarse._H2[lite]
         assert np.float16(k["inv_a"]) == np.float16(inv_a)
