@@ -64,13 +64,6 @@ constexpr bool kHidF16 = MOL_HID_F16 != 0;
 #ifndef MOL_CTL_REGS
 #define MOL_CTL_REGS 80  // measured (round 2): 48 made ptxas spill the issuer loops (LDL in front of tcgen05.mma): 35.4 -> 33.2 ms per step
 #endif
-#ifndef MOL_E1_IN_E3
-#define MOL_E1_IN_E3 0
-#endif
-// E1 (fp32 logits -> fp16 operand A2) is done by the slot's E3 warpgroup, which keeps the packed logits it needs for its own
-// weighted sum anyway, instead of by the E1/E2 group, whose chain E1 -> G2 -> E2 is the longer one of a slot (ncu round 2: the
-// E2 group waits 21 % of its time on hid_full, the E3 group 16 % on e1_done)
-constexpr bool kE1InE3 = MOL_E1_IN_E3 != 0;
 constexpr int kE2Regs = MOL_E2_REGS, kCtlRegs = MOL_CTL_REGS, kE13Regs = 240 - kE2Regs - kCtlRegs / 2;
 static_assert(256 * kE13Regs + 256 * kE2Regs + 128 * kCtlRegs <= kThreads * 96, "register pool over-committed");
 constexpr float kLog2e = 1.4426950408889634f;
@@ -457,8 +450,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             __syncwarp();
             // the next G1 overwrites LOG / A2 and reads the next query image: the E3 group must have copied the fp16
             // logits of this query out of A2 and staged that image (a2_read)
-            // (MOL_E1_IN_E3: the image is staged before e1_done is arrived, no second barrier)
-            if (!kE1InE3 && (j + 1 < n || (n_next > 0 && C::STAGES > 1))) mbar_wait_sleep(&bars->a2_read[wg], (c1 - 1u) & 1u);
+            if (j + 1 < n || (n_next > 0 && C::STAGES > 1)) mbar_wait_sleep(&bars->a2_read[wg], (c1 - 1u) & 1u);
             int g1_stage = -1;  // smem stage whose item tile the next G1 of this slot reads (-1: none to issue here)
             if (j + 1 < n) {
               g1_stage = s;
@@ -574,7 +566,7 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     bool have = seq.next(tile, q);
     while (have) {
       const bool have_next = seq.next(tile, q);
-      if (!kE1InE3) do_e1(cnt);
+      do_e1(cnt);
       // ---------------- E2
       mbar_wait_sleep(&bars->hid_full[wg], cnt & 1u);
       tc_fence_after();
@@ -689,42 +681,6 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // image buffer is free); a2_read then lets the issuer start the next G1, which overwrites both.
     auto e1 = [&](uint32_t (&pk)[L / 2]) __attribute__((always_inline)) {
       if (warp == 0) TR(0, 0, cnt);
-      if constexpr (kE1InE3) {
-        // this group converts LOG itself: fp32 chunk c (16 columns) -> pk[8c .. 8c + 8) -> A2 columns [8c, 8c + 8), which
-        // overwrite LOG columns of chunk c / 2 (already in registers)
-        mbar_wait_sleep(&bars->log_full[wg], cnt & 1u);
-        tc_fence_after();
-        if (warp == 0) TR(0, 1, cnt);
-        uint32_t la[16], lb[16];
-        auto conv = [&](const uint32_t* v, int c) __attribute__((always_inline)) {
-#pragma unroll
-          for (int j2 = 0; j2 < 8; ++j2)
-            pk[8 * c + j2] = pack_f16x2(__uint_as_float(v[2 * j2]), __uint_as_float(v[2 * j2 + 1]));
-          tmem_st_x8(base + kColLog + 8 * c, &pk[8 * c]);
-        };
-        tmem_ld_x16(base + kColLog, la);
-        tmem_ld_x16(base + kColLog + 16, lb);
-        if (have_n) store_image();  // G1 of this query is complete: the image buffer is free
-        fence_proxy_async_smem();
-        tmem_ld_wait_bind16(la);
-        tmem_ld_wait_bind16(lb);
-        conv(la, 0);
-        if constexpr (L == 64) tmem_ld_x16(base + kColLog + 32, la);
-        conv(lb, 1);
-        if constexpr (L == 64) {
-          tmem_ld_x16(base + kColLog + 48, lb);
-          tmem_ld_wait_bind16(la);
-          tmem_ld_wait_bind16(lb);
-          conv(la, 2);
-          conv(lb, 3);
-        }
-        tmem_st_x8(base + kColLog + L / 2, ones);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bars->e1_done[wg]);
-        if (warp == 0) TR(0, 2, cnt);
-        return;
-      }
       mbar_wait_sleep(&bars->e1_done[wg], cnt & 1u);
       tc_fence_after();
       if (warp == 0) TR(0, 1, cnt);
@@ -1046,8 +1002,7 @@ static void* g_trace = nullptr;
 #define MOL_STR2(x) #x
 #define MOL_STR(x) MOL_STR2(x)
 const char* coarse_build_knobs() {
-  return "e2poly=" MOL_STR(MOL_E2_POLY_MASK) " e2h2=" MOL_STR(MOL_E2_H2_MASK) " hidf16=" MOL_STR(MOL_HID_F16)
-         " e1ine3=" MOL_STR(MOL_E1_IN_E3);
+  return "e2poly=" MOL_STR(MOL_E2_POLY_MASK) " e2h2=" MOL_STR(MOL_E2_H2_MASK) " hidf16=" MOL_STR(MOL_HID_F16);
 }
 
 void* coarse_trace_buffer() { return g_trace; }

@@ -38,7 +38,7 @@ def test_default_build_reports_the_shipped_kernel_knobs():
     if os.environ.get("MOL_B200_LIB"):
         pytest.skip("a tuning variant is loaded")
     k = _lib.build_knobs()
-    assert k == {"e2poly": 0, "e2h2": 0x3E, "hidf16": 1, "e1ine3": 0}
+    assert k == {"e2poly": 0, "e2h2": 0x3E, "hidf16": 1}
 
 
 def test_constants_match_header():
