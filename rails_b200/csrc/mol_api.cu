@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "mol_coarse.cuh"
+#include "mol_dotfilter.cuh"
 
 namespace mol {
 
@@ -792,16 +793,20 @@ __global__ void avg_groups_kernel(const float* __restrict__ in, float* __restric
 }
 
 struct AvgWs {
+  int32_t* stats;  // 8 x int32 at offset 0 (mol_search_stats): counters of the streaming prefilter (mol_dotfilter.cuh)
   float *pre, *h, *proj, *hq, *qsub, *gq, *w1t, *w2t, *qsum, *scores, *seg_scores, *exact;
   int32_t *seg_idx, *cand_idx;
   float* cand_scores;
   int rows;
+  int filter;      // the streaming dot-product top-k serves the prefilter
+  DotTopkPlan dp;
   size_t total;
 };
 
 static int plan_avg(const mol_shape_t& s, int64_t N, int B, int k, int avg_top_k, void* base, size_t cap, AvgWs* ws) {
   Dims D = dims_of(s);
   Arena a(base, cap);
+  ws->stats = a.take<int32_t>(kNumStats);
   ws->pre = a.take<float>((size_t)B * 2 * D.Hq);
   ws->h = a.take<float>((size_t)B * D.Hq);
   ws->proj = a.take<float>((size_t)B * D.Pq_proj * D.d);
@@ -824,6 +829,8 @@ static int plan_avg(const mol_shape_t& s, int64_t N, int B, int k, int avg_top_k
   ws->cand_idx = a.take<int32_t>((size_t)B * avg_top_k);
   ws->exact = a.take<float>((size_t)B * avg_top_k);
   (void)k;
+  ws->filter = dot_topk_eligible(N, B, D.d, avg_top_k) ? 1 : 0;
+  if (ws->filter) dot_topk_plan(a, N, B, D.d, avg_top_k, ws->scores, ws->rows, &ws->dp);
   ws->total = align_up(a.off, 256);
   if (base != nullptr && a.off > cap) {
     set_error("workspace too small: need %zu bytes, got %zu", ws->total, cap);
@@ -887,7 +894,12 @@ int mol_search_avg(const mol_shape_t* shape, const mol_weights_t* w, const mol_i
     avg_groups_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.qsub, ws.qsum, B, D.Pq, D.d, 1.0f);
     MOL_LAUNCH_CHECK();
   }
-  for (int b0 = 0; b0 < B; b0 += ws.rows) {
+  MOL_CUDA(cudaMemsetAsync(ws.stats, 0, kNumStats * sizeof(int32_t), st));
+  const bool stream_prefilter = ws.filter && dot_topk_aligned(avg_items, D.d, 0, ws.qsum, D.d);
+  if (stream_prefilter)  // |avg_items[x]| <= 1: a mean of l2-normalised sub-embeddings
+    MOL_TRY(dot_topk_run(ws.dp, avg_items, D.d, 0, D.d, nullptr, 1.0f, ws.qsum, D.d, ws.cand_scores, ws.cand_idx, nullptr,
+                         nullptr, ws.stats, st));
+  for (int b0 = 0; b0 < B && !stream_prefilter; b0 += ws.rows) {
     const int nb = (B - b0 < ws.rows) ? (B - b0) : ws.rows;
     // avg_sim_values = q_sum . avg_items^T ; top avg_top_k positions per query (:352-360)
     MOL_TRY(launch_linear(ws.qsum + (size_t)b0 * D.d, avg_items, nullptr, ws.scores, nb, (int)N, D.d, D.d, 1, ACT_NONE, st));
@@ -966,9 +978,12 @@ __global__ void mask_duplicates_kernel(const int32_t* __restrict__ sorted_idx, f
 }
 
 struct GroupsWs {
-  float *pre, *h, *proj, *hq, *qsub, *gq, *w1t, *w2t, *qavg, *scores, *seg_scores, *sel_scores, *exact;
+  int32_t* stats;  // 8 x int32 at offset 0 (mol_search_stats): counters of the streaming selections (mol_dotfilter.cuh)
+  float *pre, *h, *proj, *hq, *qsub, *gq, *w1t, *w2t, *qavg, *scores, *seg_scores, *sel_scores, *exact, *dsel;
   int32_t *seg_idx, *group_idx, *avg_idx, *sorted_idx;
   int rows;  // rows of the (rows, N) dot-product matrix scored per launch (a multiple of P_Q)
+  int filter_groups, filter_avg;  // the streaming dot-product top-k serves the per-group / the averaged selection
+  DotTopkPlan dp_groups, dp_avg;
   size_t total;
 };
 
@@ -976,6 +991,7 @@ static int plan_groups(const mol_shape_t& s, int64_t N, int B, int kpg, int avg_
                        GroupsWs* ws) {
   Dims D = dims_of(s);
   Arena a(base, cap);
+  ws->stats = a.take<int32_t>(kNumStats);
   ws->pre = a.take<float>((size_t)B * 2 * D.Hq);
   ws->h = a.take<float>((size_t)B * D.Hq);
   ws->proj = a.take<float>((size_t)B * D.Pq_proj * D.d);
@@ -1002,6 +1018,11 @@ static int plan_groups(const mol_shape_t& s, int64_t N, int B, int kpg, int avg_
   ws->avg_idx = a.take<int32_t>((size_t)B * (avg_top_k > 0 ? avg_top_k : 1));
   ws->sorted_idx = a.take<int32_t>((size_t)B * C);
   ws->exact = a.take<float>((size_t)B * C);
+  ws->dsel = a.take<float>((size_t)B * (D.Pq * kpg > avg_top_k ? D.Pq * kpg : avg_top_k));
+  ws->filter_groups = dot_topk_eligible(N, B * D.Pq, D.d, kpg) ? 1 : 0;
+  if (ws->filter_groups) dot_topk_plan(a, N, B * D.Pq, D.d, kpg, ws->scores, ws->rows, &ws->dp_groups);
+  ws->filter_avg = (avg_top_k > 0 && dot_topk_eligible(N, B, D.d, avg_top_k)) ? 1 : 0;
+  if (ws->filter_avg) dot_topk_plan(a, N, B, D.d, avg_top_k, ws->scores, ws->rows, &ws->dp_avg);
   ws->total = align_up(a.off, 256);
   if (base != nullptr && a.off > cap) {
     set_error("workspace too small: need %zu bytes, got %zu", ws->total, cap);
@@ -1072,7 +1093,16 @@ int mol_search_groups(const mol_shape_t* shape, const mol_weights_t* w, const mo
   // rows (b, n) of Q_sub against X_sub[:, m, :] (row stride P_X * d inside the fp32 cache)
   const int per_m = D.Pq * k_per_group;
   const int qrows = ws.rows / D.Pq;  // queries per launch
+  MOL_CUDA(cudaMemsetAsync(ws.stats, 0, kNumStats * sizeof(int32_t), st));
+  // streaming selection (tcgen05 tf32 pass + threshold filter + fp32 rescoring, no (rows, N) matrix; X_sub rows have
+  // norm <= 1) when the sizes allow it, else the materialised matrix + radix select
+  const bool stream_groups = ws.filter_groups && dot_topk_aligned(index->xsub_f32, (int64_t)D.Px * D.d, 0, ws.qsub, D.d);
   for (int m = 0; m < D.Px; ++m) {
+    if (stream_groups) {
+      MOL_TRY(dot_topk_run(ws.dp_groups, index->xsub_f32, (int64_t)D.Px * D.d, m * D.d, D.d, nullptr, 1.0f, ws.qsub, D.d,
+                           ws.dsel, ws.group_idx + (size_t)m * B * per_m, nullptr, nullptr, ws.stats, st));
+      continue;
+    }
     for (int b0 = 0; b0 < B; b0 += qrows) {
       const int nq = (B - b0 < qrows) ? (B - b0) : qrows;
       const int nb = nq * D.Pq;
@@ -1085,7 +1115,11 @@ int mol_search_groups(const mol_shape_t* shape, const mol_weights_t* w, const mo
     const int64_t total = (int64_t)B * D.d;
     avg_groups_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.qsub, ws.qavg, B, D.Pq, D.d, 1.0f / D.Pq);
     MOL_LAUNCH_CHECK();
-    for (int b0 = 0; b0 < B; b0 += ws.rows) {
+    const bool stream_avg = ws.filter_avg && dot_topk_aligned(avg_items, D.d, 0, ws.qavg, D.d);
+    if (stream_avg)
+      MOL_TRY(dot_topk_run(ws.dp_avg, avg_items, D.d, 0, D.d, nullptr, 1.0f, ws.qavg, D.d, ws.dsel, ws.avg_idx, nullptr,
+                           nullptr, ws.stats, st));
+    for (int b0 = 0; b0 < B && !stream_avg; b0 += ws.rows) {
       const int nb = (B - b0 < ws.rows) ? (B - b0) : ws.rows;
       MOL_TRY(launch_linear(ws.qavg + (size_t)b0 * D.d, avg_items, nullptr, ws.scores, nb, (int)N, D.d, D.d, 1, ACT_NONE, st));
       MOL_TRY(select_positions(ws, N, nb, avg_top_k, ws.avg_idx + (size_t)b0 * avg_top_k, st));

@@ -9,6 +9,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "mol_dotfilter.cuh"
 
 namespace mol {
 
@@ -129,15 +130,50 @@ int mol_select_valid(const float* scores, const int64_t* ids, const int64_t* inv
   return MOL_OK;
 }
 
-int mol_mips_workspace_bytes(int64_t num_items, int32_t B, int32_t k, size_t* bytes) {
-  MOL_CHECK_ARG(bytes && num_items >= 0 && B >= 0 && k >= 1, "bad arguments");
+namespace {
+// Workspace of mol_mips_search: 8 x int32 stats (mol_search_stats reads them back) | (rows, N) fp32 matrix of the
+// materialising path (also the fallback / sample matrix of the streaming path) | select scratch | streaming-path buffers.
+struct MipsWs {
+  int32_t* stats;
+  float* mat;
+  char* tk;
+  size_t tk_bytes;
+  int rows;
+  int filter;  // sizes allow the streaming path (D is not known when the workspace is measured: checked again per call)
+  mol::DotTopkPlan dp;
+  size_t total;
+};
+int plan_mips(int64_t num_items, int32_t B, int32_t k, void* base, size_t cap, MipsWs* ws) {
+  using namespace mol;
+  Arena a(base, cap);
   const int64_t n = num_items > 0 ? num_items : 1;
+  const int Bq = B > 0 ? B : 1;
   int64_t rows = (int64_t)score_matrix_budget() / (int64_t)(sizeof(float) * (size_t)n);
   if (rows < 1) rows = 1;
-  if (rows > B) rows = B > 0 ? B : 1;
+  if (rows > Bq) rows = Bq;
+  ws->rows = (int)rows;
+  ws->stats = a.take<int32_t>(8);
+  ws->mat = a.take<float>((size_t)rows * (size_t)n);
   size_t topk;
   MOL_TRY(mol_topk_workspace_bytes(num_items, (int32_t)rows, k, &topk));
-  *bytes = align_up((size_t)rows * (size_t)n * sizeof(float), 256) + topk + 512;
+  ws->tk_bytes = topk + 256;
+  ws->tk = a.take<char>(ws->tk_bytes);
+  ws->filter = dot_topk_eligible(num_items, Bq, 32, k) ? 1 : 0;
+  if (ws->filter) dot_topk_plan(a, num_items, Bq, 32, k, ws->mat, ws->rows, &ws->dp);
+  ws->total = align_up(a.off, 256);
+  if (base != nullptr && a.off > cap) {
+    set_error("mips workspace too small: need %zu, got %zu", ws->total, cap);
+    return MOL_ERR_WORKSPACE;
+  }
+  return MOL_OK;
+}
+}  // namespace
+
+int mol_mips_workspace_bytes(int64_t num_items, int32_t B, int32_t k, size_t* bytes) {
+  MOL_CHECK_ARG(bytes && num_items >= 0 && B >= 0 && k >= 1, "bad arguments");
+  MipsWs ws;
+  MOL_TRY(plan_mips(num_items, B, k, nullptr, 0, &ws));
+  *bytes = ws.total + 256;
   return MOL_OK;
 }
 
@@ -163,18 +199,20 @@ int mol_mips_search(const float* items, const int64_t* item_ids, const float* qu
   }
   if (B == 0) return MOL_OK;
   MOL_CHECK_ARG(items && queries && out_scores && out_ids && workspace, "NULL buffer");
-  size_t need;
-  MOL_TRY(mol_mips_workspace_bytes(num_items, B, k, &need));
-  if (workspace_bytes < need) {
-    set_error("mips workspace too small: need %zu, got %zu", need, workspace_bytes);
-    return MOL_ERR_WORKSPACE;
-  }
-  int64_t rows = (int64_t)score_matrix_budget() / (int64_t)(sizeof(float) * (size_t)num_items);
-  if (rows < 1) rows = 1;
-  if (rows > B) rows = B;
-  float* mat = static_cast<float*>(workspace);
-  char* tk = static_cast<char*>(workspace) + align_up((size_t)rows * (size_t)num_items * sizeof(float), 256);
-  const size_t tk_bytes = workspace_bytes - (size_t)(tk - static_cast<char*>(workspace));
+  MOL_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 256 == 0, "workspace must be 256-byte aligned");
+  MipsWs ws;
+  MOL_TRY(plan_mips(num_items, B, k, workspace, workspace_bytes, &ws));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MOL_CUDA(cudaMemsetAsync(ws.stats, 0, 8 * sizeof(int32_t), st));
+  // streaming path (f4 "fused GEMM + top-k"): tcgen05 tf32 pass + threshold filter + fp32 rescoring of the survivors, no
+  // (B, N) matrix - see mol_dotfilter.cuh
+  if (ws.filter && dot_topk_eligible(num_items, B, D, k) && dot_topk_aligned(items, D, 0, queries, D))
+    return dot_topk_run(ws.dp, items, D, 0, D, nullptr, 0.f, queries, D, out_scores, nullptr, out_ids, item_ids, ws.stats,
+                        st);
+  const int64_t rows = ws.rows;
+  float* mat = ws.mat;
+  char* tk = ws.tk;
+  const size_t tk_bytes = ws.tk_bytes;
   for (int b0 = 0; b0 < B; b0 += (int)rows) {
     const int nb = (B - b0 < rows) ? (B - b0) : (int)rows;
     MOL_TRY(mol_dot_scores(items, queries + (size_t)b0 * D, num_items, D, nb, mat, stream));

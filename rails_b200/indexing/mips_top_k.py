@@ -1,6 +1,8 @@
 """Exact MIPS top-k, B200-native drop-in for rails/indexing/mips_top_k.py (`MIPSTopKModule` :24-39,
 `MIPSBruteForceTopK` :41-81): fp32 q . items^T over the whole corpus + row-wise top-k + id gather, all in
-libmol_b200.so (`mol_mips_search`).  SURVEY.md §8 row f4."""
+libmol_b200.so (`mol_mips_search`).  Large corpora (>= 64k items, D a multiple of 32) take the streaming path: a tcgen05
+tf32 pass with a fused threshold filter, fp32 rescoring of the survivors and a per-query completeness proof - the fused
+GEMM + top-k of SURVEY.md §8 row f4; the returned scores and ids are those of the fp32 computation."""
 from __future__ import annotations
 
 import ctypes
@@ -45,6 +47,18 @@ class MIPSBruteForceTopK(MIPSTopKModule):
             self._items = e.squeeze(0).detach().to(torch.float32).contiguous()
             self._ids = i.reshape(-1).detach().to(device=self._items.device, dtype=torch.int64).contiguous()
             self._key = key
+
+    def last_search_stats(self) -> dict:
+        """Counters of the last forward(): `filter_strategy` = 1 when the streaming tcgen05 path ran (no (B, N) matrix),
+        `fallback_queries` = queries re-done by the plain fp32 pass, `filter_overflows`, `max_survivors`."""
+        if self._ws is None:
+            raise RuntimeError("forward() has not been called yet")
+        lib = _lib.load()
+        out = (ctypes.c_int32 * _lib.NUM_STATS)()
+        dev = self._ws.device
+        with torch.cuda.device(dev):
+            _lib.check(lib.mol_search_stats(engine._ptr(self._ws), out, engine._stream_ptr(dev)))
+        return dict(zip(_lib.STAT_NAMES, (int(v) for v in out)))
 
     @torch.no_grad()
     def forward(self, query_embeddings: torch.Tensor, k: int, sorted: bool = True, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:

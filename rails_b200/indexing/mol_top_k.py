@@ -165,6 +165,11 @@ class MoLAvgTopK(MoLTopKModule):
         self._avg_items = None
         self._avg_key = None
 
+    def last_search_stats(self) -> dict:
+        """Counters of the last forward(): `filter_strategy` = 1 when the streaming tcgen05 prefilter ran (mol_dotfilter),
+        `fallback_queries` = prefilter rows re-done by the plain fp32 pass, `filter_overflows`, `max_survivors`."""
+        return engine.search_stats(self._mol_module.workspace(self._ensure_index().device))
+
     def _ensure_avg(self):
         index = self._ensure_index()
         if self._avg_items is None or self._avg_key is not self._index:
@@ -211,6 +216,10 @@ class MoLNaiveTopK(MoLTopKModule):
         )
         self._k_per_group: int = int(k_per_group)
         self._use_faiss: bool = False
+
+    def last_search_stats(self) -> dict:
+        """Counters of the last forward() (see MoLAvgTopK.last_search_stats); rows = (query, query group, item group)."""
+        return engine.search_stats(self._mol_module.workspace(self._ensure_index().device))
 
     @torch.no_grad()
     def forward(self, query_embeddings: torch.Tensor, k: int, sorted: bool = True, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -1,0 +1,125 @@
+"""GPU tests of the streaming dot-product top-k (rails_b200/csrc/mol_dotfilter_sm100.cu): the fused GEMM + top-k of
+SURVEY.md §8 row f4 (MIPSBruteForceTopK, rails/indexing/mips_top_k.py:74-81) and the streaming prefilters of row f3
+(MoLAvgTopK / MoLNaiveTopK / MoLCombTopK, rails/indexing/mol_top_k.py:239-249, :352-360, :501-511).
+
+The bar is bit-exactness: the streaming path re-scores its survivors with the same k-ascending fp32 fmaf chain as the
+materialised-matrix path, proves per row that no item outside the survivors can reach the top-k, and breaks ties by
+position - so ids AND scores must equal the materialised path (MOL_B200_DOTFILTER=0) exactly, and torch's own fp32
+result tie-aware."""
+import pytest
+import torch
+
+from tests.helpers import CFG_8x8x32, CFG_8x4x128, build_module, synthetic_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _mips(items, ids, q, k, monkeypatch, stream: bool):
+    from rails_b200.indexing.mips_top_k import MIPSBruteForceTopK
+
+    monkeypatch.setenv("MOL_B200_DOTFILTER", "1" if stream else "0")
+    top = MIPSBruteForceTopK(items.unsqueeze(0), ids.unsqueeze(0))
+    s, i = top(q, k=k)
+    torch.cuda.synchronize()
+    return s, i, top.last_search_stats()
+
+
+def _check_vs_torch(items, ids, q, k, s, i):
+    ref = q.double() @ items.double().t()  # fp64 referee: classifies fp32 near-ties
+    rs, ri = ref.topk(k, dim=1)
+    got = torch.gather(ref, 1, (i - 1))  # ids are positions + 1 in these tests
+    # every returned item scores (fp64) within fp32 noise of the fp64 top-k at the same rank
+    assert (got - rs).abs().max().item() < 2e-5
+    assert (s.double() - got).abs().max().item() < 2e-5
+    assert bool((s[:, 1:] <= s[:, :-1]).all())
+
+
+@pytest.mark.parametrize(
+    "N,D,B,k",
+    [
+        (300_000, 64, 70, 100),     # one column chunk, rows padded to 128
+        (262_144 + 77, 64, 300, 100),  # two column chunks, ragged last item tile
+        (200_000, 32, 257, 10),     # K = 32 (one box per tile)
+        (131_072, 128, 33, 200),    # K = 128
+        (100_000, 256, 130, 50),    # K = 256: 128 query rows per launch
+        (1_000_000, 64, 1, 1),      # one query, k = 1
+    ],
+)
+def test_mips_streaming_equals_materialised(N, D, B, k, monkeypatch):
+    g = torch.Generator(device=DEV).manual_seed(N + D + B)
+    items = 0.02 * torch.randn((N, D), device=DEV, generator=g)
+    q = torch.nn.functional.layer_norm(torch.randn((B, D), device=DEV, generator=g), (D,))
+    ids = torch.arange(1, N + 1, device=DEV)
+    s1, i1, st1 = _mips(items, ids, q, k, monkeypatch, True)
+    s0, i0, st0 = _mips(items, ids, q, k, monkeypatch, False)
+    assert st1["filter_strategy"] == 1 and st0["filter_strategy"] == 0
+    assert st1["fallback_queries"] == 0 and st1["filter_overflows"] == 0, st1
+    assert torch.equal(i1, i0)
+    assert torch.equal(s1, s0)
+    _check_vs_torch(items, ids, q, k, s1, i1)
+
+
+def test_mips_streaming_adversarial_rows_fall_back_and_stay_exact(monkeypatch):
+    """Rows the filter cannot serve must come out of the fallback unchanged: a zero query (every value ties at 0: the
+    survivor buffer overflows), a query whose best items all sit in ONE item tile that the strided sample never sees
+    while everything else scores lower (fine), duplicated items (ties at the top), and a corpus sorted by norm."""
+    N, D, B, k = 200_000, 64, 6, 100
+    g = torch.Generator(device=DEV).manual_seed(5)
+    items = 0.02 * torch.randn((N, D), device=DEV, generator=g)
+    order = items.norm(dim=1).argsort()
+    items = items[order].contiguous()          # sorted by norm: the big scores cluster at the end
+    items[1000:1100] = items[150_000:150_100]  # exact duplicates
+    q = torch.nn.functional.layer_norm(torch.randn((B, D), device=DEV, generator=g), (D,))
+    q[0] = 0.0                                 # all-zero query
+    q[1] = 50.0 * items[199_999] / items[199_999].norm()
+    ids = torch.arange(1, N + 1, device=DEV)
+    s1, i1, st1 = _mips(items, ids, q, k, monkeypatch, True)
+    s0, i0, _ = _mips(items, ids, q, k, monkeypatch, False)
+    assert st1["filter_strategy"] == 1
+    assert st1["fallback_queries"] >= 1 and st1["filter_overflows"] >= 1, st1  # the zero query
+    assert st1["fallback_queries"] <= 2, st1
+    # (the zero query ties all 200k items at 0: which 100 of them a select keeps is unspecified, as with torch.topk)
+    assert torch.equal(i1[1:], i0[1:])
+    assert torch.equal(s1, s0)
+    assert bool((s1[0] == 0).all()) and i1[0].unique().numel() == k and int(i1[0].min()) >= 1 and int(i1[0].max()) <= N
+
+
+def test_mips_small_or_odd_shapes_keep_the_materialised_path(monkeypatch):
+    g = torch.Generator(device=DEV).manual_seed(9)
+    for N, D in ((3883, 50), (100_000, 50), (20_000, 64)):
+        items = 0.02 * torch.randn((N, D), device=DEV, generator=g)
+        q = torch.randn((4, D), device=DEV, generator=g)
+        ids = torch.arange(1, N + 1, device=DEV)
+        s, i, st = _mips(items, ids, q, 10, monkeypatch, True)
+        assert st["filter_strategy"] == 0
+        _check_vs_torch(items, ids, q, 10, s, i)
+
+
+@pytest.mark.parametrize("cfg,N,B", [(CFG_8x8x32, 200_000, 24), (CFG_8x4x128, 70_000, 40)])
+def test_approximate_modules_streaming_equals_materialised(cfg, N, B, monkeypatch):
+    """MoLAvgTopK / MoLNaiveTopK / MoLCombTopK: the streaming prefilters select exactly the candidates the materialised
+    (rows, N) matrices select, so the final (scores, ids) are identical."""
+    from rails_b200.indexing.mol_top_k import MoLAvgTopK, MoLCombTopK, MoLNaiveTopK
+
+    mol, _ = build_module(cfg, None, DEV, seed=21)
+    items, ids, q, uid = synthetic_inputs(cfg, N, B, 21, DEV)
+    kw = {"user_ids": uid} if uid is not None else {}
+    makers = (
+        lambda: MoLAvgTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), 500),
+        lambda: MoLNaiveTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), 5),
+        lambda: MoLCombTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), 200, 3),
+    )
+    for make in makers:
+        out = {}
+        for stream in (True, False):
+            monkeypatch.setenv("MOL_B200_DOTFILTER", "1" if stream else "0")
+            top = make()
+            s, i = top(q, k=10, **kw)
+            torch.cuda.synchronize()
+            out[stream] = (s, i, top.last_search_stats())
+        st = out[True][2]
+        assert st["filter_strategy"] == 1 and out[False][2]["filter_strategy"] == 0, st
+        assert st["filter_overflows"] == 0, st
+        assert torch.equal(out[True][1], out[False][1]), type(top).__name__
+        assert torch.equal(out[True][0], out[False][0]), type(top).__name__
