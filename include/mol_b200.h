@@ -206,6 +206,15 @@ int mol_mips_workspace_bytes(int64_t num_items, int32_t B, int32_t k, size_t* by
 int mol_mips_search(const float* items, const int64_t* item_ids, const float* queries, int64_t num_items,
                     int32_t D, int32_t B, int32_t k, float* out_scores, int64_t* out_ids, void* workspace,
                     size_t workspace_bytes, mol_stream_t stream);
+/* The same search with a caller-kept bound on the item norms: item_norm_cache = 2 device floats, {-1, 0} when the items
+ * are new or have changed; the first call fills it (one pass over the items), later calls skip that pass.  The streaming
+ * path (>= 64k items, D a multiple of 32: tcgen05 tf32 pass + threshold filter + fp32 rescoring, no (B, N) matrix) needs
+ * the bound for its per-query completeness test; NULL = recomputed by every call.  Workspace: mol_mips_workspace_bytes;
+ * mol_search_stats() on it reports [0] queries re-done by the plain fp32 pass, [1] survivor-buffer overflows, [2] max
+ * survivors, [3] 1 when the streaming path ran. */
+int mol_mips_search_cached(const float* items, const int64_t* item_ids, const float* queries, int64_t num_items,
+                           int32_t D, int32_t B, int32_t k, float* item_norm_cache, float* out_scores,
+                           int64_t* out_ids, void* workspace, size_t workspace_bytes, mol_stream_t stream);
 /* DotProductSimilarity.forward, (1, X, D) branch (rails/similarities/dot_product_similarity_fn.py:46-51): (B, N) fp32. */
 int mol_dot_scores(const float* items, const float* queries, int64_t num_items, int32_t D, int32_t B,
                    float* out_scores, mol_stream_t stream);

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "mol_index_build_workspace_bytes", "mol_index_build", "mol_search_workspace_bytes", "mol_search",
     "mol_search_host", "mol_score_all", "mol_score_all_coarse", "mol_query_prologue", "mol_merge_topk_workspace_bytes",
     "mol_merge_topk", "mol_topk_workspace_bytes", "mol_topk", "mol_launch_count", "mol_launch_count_reset",
-    "mol_profile_enable", "mol_profile_collect", "mol_select_valid", "mol_mips_workspace_bytes", "mol_mips_search",
+    "mol_profile_enable", "mol_profile_collect", "mol_select_valid", "mol_mips_workspace_bytes", "mol_mips_search", "mol_mips_search_cached",
     "mol_dot_scores", "mol_index_avg_embeddings", "mol_search_avg_workspace_bytes", "mol_search_avg",
     "mol_search_groups_workspace_bytes", "mol_search_groups",
     "mol_weights_prepared_bytes", "mol_weights_prepare", "mol_search_stats",
@@ -138,6 +138,10 @@ def load() -> ctypes.CDLL:
     lib.mol_mips_workspace_bytes.argtypes = [c_int64, c_int32, c_int32, P(c_size_t)]
     lib.mol_mips_search.argtypes = [
         c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
+    ]
+    lib.mol_mips_search_cached.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+        c_void_p,
     ]
     lib.mol_dot_scores.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]
     lib.mol_index_avg_embeddings.argtypes = [P(MolShape), P(MolIndex), c_void_p, c_void_p]

@@ -42,6 +42,10 @@ struct DotTopkPlan {
 // reports MOL_ERR_INVALID for a misaligned matrix - callers test dot_topk_aligned first).
 bool dot_topk_eligible(int64_t N, int R, int K, int kk);
 bool dot_topk_aligned(const float* items, int64_t pitch, int col0, const float* Q, int64_t q_pitch);
+// Row-norm bound kept by the caller across calls: cache = 2 device floats {bound or < 0 when not yet computed, accumulator
+// (0 on reset)}.  Computes max_x |x[col0 : col0 + K]|_2 into cache[0] when it is negative (one pass over the items), else
+// two idle launches.  Pass `cache` as xmax_dev afterwards.
+int dot_topk_norm_cache(const float* items, int64_t N, int64_t pitch, int col0, int K, float* cache, cudaStream_t st);
 // Carves the buffers of one dot_topk_run out of `a` (measures only when a.base == nullptr).  `fb_scores` / `fb_rows`: the
 // caller's existing (rows, N) fp32 score matrix (shared with its non-streaming path), or nullptr to take one here.
 void dot_topk_plan(Arena& a, int64_t N, int R, int K, int kk, float* fb_scores, int fb_rows, DotTopkPlan* p);

@@ -1,12 +1,13 @@
 // Streaming dot-product top-k on the sm_100a tensor cores (interface and the proof of exactness: mol_dotfilter.cuh).
 //
-// dot_filter_kernel - one persistent CTA per SM, 192 threads:
+// dot_filter_kernel - one persistent CTA per SM, 320 threads:
 //   warp 0      TMA producer: the <= 256 query rows of this launch once (K / 32 boxes of cc rows x 32 fp32, SWIZZLE_128B),
 //               then the item tiles (128 rows) box by box through a ring of 16 KB stages;
 //   warp 1      MMA issuer: per box 4 x tcgen05.mma kind::tf32 (M = 128 items, N = cc query rows, K = 8) into one of two
 //               256-column TMEM accumulators; tcgen05.commit frees the stage, and after the last box of a tile announces
 //               the accumulator;
-//   warps 2..5  epilogue: TMEM lane = item row, 32 columns per tcgen05.ld; sample mode stores the values (column-major:
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, each half of the columns): TMEM lane = item row, 32 columns
+//               per tcgen05.ld; sample mode stores the values (column-major:
 //               coalesced over the 32 lanes), filter mode compares against the per-column levels in shared memory and
 //               appends the rare survivors (atomic counter per query row).
 // The fp32 operands are consumed as they are (tf32 reads the upper 19 bits); HBM traffic = the item matrix once per
@@ -24,7 +25,9 @@ using namespace sm100;
 namespace {
 
 constexpr int DF_TILE = 128;
-constexpr int DF_THREADS = 192;
+constexpr int DF_EPI_WARPS = 8;  // two per SM sub-partition: one's tcgen05.ld / branch latencies hide behind the other
+constexpr int DF_EPI_THREADS = DF_EPI_WARPS * 32;
+constexpr int DF_THREADS = 64 + DF_EPI_THREADS;
 constexpr int DF_MAX_STAGES = 6;
 constexpr int DF_BOX_BYTES = DF_TILE * 128;  // 128 rows x 32 fp32
 constexpr int DF_MAX_CC = 256;
@@ -59,7 +62,13 @@ struct DfBars {
   int staged;  // entries in the survivor staging buffer (may run past DF_STAGE_CAP: the excess went straight to global)
 };
 
-__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(DF_EPI_THREADS) : "memory"); }
+// the per-column levels never change during a launch: a plain (non-volatile) shared-memory load the compiler may reorder
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 r;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
 
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4)                      // D format = F32
@@ -118,7 +127,7 @@ dot_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     bars->staged = 0;
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->acc_full[a], 1);
-      mbar_init(&bars->acc_empty[a], 128);
+      mbar_init(&bars->acc_empty[a], DF_EPI_THREADS);
     }
     fence_mbar_init();
   }
@@ -183,16 +192,19 @@ dot_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5) ===============================
+    // =============================== epilogue (warps 2..9) ===============================
     const int quarter = warp & 3;  // TMEM lanes this warp may read
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int nch = P.cc / 32;  // even (cc % 64 == 0)
+    const int half = (warp - 2) >> 2;  // which half of the column chunks this warp takes
+    const int c_lo = half * (nch / 2), c_hi = c_lo + nch / 2;
+    const uint32_t sLevel_a = smem_u32(sLevel);
     const int etid = tid - 64;
     auto drain = [&]() {
       epilogue_bar_sync();
       int n = bars->staged;
       if (n > DF_STAGE_CAP) n = DF_STAGE_CAP;
-      for (int e = etid; e < n; e += 128) {
+      for (int e = etid; e < n; e += DF_EPI_THREADS) {
         const int col = sStageCol[e];
         const int slot = atomicAdd(P.cnt + col, 1);
         if (slot < P.cap) {
@@ -224,11 +236,11 @@ dot_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // (each epilogue warp is alone on its SM sub-partition: every dependent instruction and every branch costs its
           // full latency, so the test runs as four independent predicate chains and the rare hit is extracted without a
           // branch per column)
-          const float4* lv = reinterpret_cast<const float4*>(sLevel + cbase);
+          const uint32_t lv = sLevel_a + (uint32_t)cbase * 4u;
           bool a0 = false, a1 = false, a2 = false, a3 = false;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 t = lv[j4];
+            const float4 t = lds_f4(lv + 16u * j4);
             a0 |= __uint_as_float(v[4 * j4 + 0]) >= t.x;
             a1 |= __uint_as_float(v[4 * j4 + 1]) >= t.y;
             a2 |= __uint_as_float(v[4 * j4 + 2]) >= t.z;
@@ -256,7 +268,7 @@ dot_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               float fv = 0.f;
 #pragma unroll
               for (int j4 = 7; j4 >= 0; --j4) {
-                const float4 t = lv[j4];
+                const float4 t = lds_f4(lv + 16u * j4);
                 const float tt[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                 for (int u = 3; u >= 0; --u) {
@@ -274,14 +286,16 @@ dot_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       };
       uint32_t va[32], vb[32];
-      tmem_ld_x32(taddr, va);
-      for (int c = 0; c < nch; c += 2) {
+      tmem_ld_x32(taddr + (uint32_t)c_lo * 32u, va);
+      for (int c = c_lo; c < c_hi; c += 2) {  // (every condition is warp-uniform)
         tmem_ld_wait_bind32(va);
-        tmem_ld_x32(taddr + (uint32_t)(c + 1) * 32u, vb);
+        if (c + 1 < c_hi) tmem_ld_x32(taddr + (uint32_t)(c + 1) * 32u, vb);
         consume(va, c * 32);
-        tmem_ld_wait_bind32(vb);
-        if (c + 2 < nch) tmem_ld_x32(taddr + (uint32_t)(c + 2) * 32u, va);
-        consume(vb, (c + 1) * 32);
+        if (c + 1 < c_hi) {
+          tmem_ld_wait_bind32(vb);
+          if (c + 2 < c_hi) tmem_ld_x32(taddr + (uint32_t)(c + 2) * 32u, va);
+          consume(vb, (c + 1) * 32);
+        }
       }
       tc_fence_before();
       mbar_arrive(&bars->acc_empty[acc]);
@@ -301,7 +315,9 @@ dot_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // *out = max over rows of |x[col0 : col0 + K]|_2 (non-negative floats order like their bit patterns).  K / 4 <= 32: a group
 // of K / 4 lanes owns a row (one float4 each, 512 contiguous bytes per warp when the rows are dense); else a warp per row.
 __global__ void __launch_bounds__(256)
-row_norm_max_kernel(const float* __restrict__ items, int64_t N, int64_t pitch, int col0, int K, float* __restrict__ out) {
+row_norm_max_kernel(const float* __restrict__ items, int64_t N, int64_t pitch, int col0, int K, float* __restrict__ out,
+                    const float* __restrict__ skip_if_valid) {
+  if (skip_if_valid != nullptr && skip_if_valid[0] >= 0.f) return;  // a cached bound exists
   const int lane = threadIdx.x & 31;
   const int k4 = K / 4;
   const int lpr = k4 < 32 ? k4 : 32;  // lanes per row (8, 16, 24, 32; K % 32 == 0)
@@ -333,6 +349,10 @@ row_norm_max_kernel(const float* __restrict__ items, int64_t N, int64_t pitch, i
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
   if (lane == 0 && best > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(best) * 1.000001f));
+}
+
+__global__ void norm_publish_kernel(float* cache) {
+  if (cache[0] < 0.f) cache[0] = cache[1];
 }
 
 // level[r] = m-th largest sampled value of row r; check[r] = level[r] + E_r with E_r = 2^-8 |q_r| xmax: every item whose
@@ -518,7 +538,7 @@ struct Sizes {
 };
 Sizes sizes_of(int64_t N, int kk) {
   Sizes z;
-  z.T = 4 * kk > 512 ? 4 * kk : 512;                  // survivors aimed at
+  z.T = 4 * kk > 256 ? 4 * kk : 256;                  // survivors aimed at
   z.cap = z.T <= 4096 ? 4 * z.T : 2 * z.T;            // survivor capacity (the count's relative spread is ~ 1 / sqrt(m))
   const int64_t tiles = (N + DF_TILE - 1) / DF_TILE;
   int64_t s_target = N / 8 < 32768 ? N / 8 : 32768;
@@ -529,7 +549,7 @@ Sizes sizes_of(int64_t N, int kk) {
   if (z.stride < 1) z.stride = 1;
   z.S = nst * DF_TILE;
   int64_t m = ((int64_t)z.T * z.S + N - 1) / N;
-  if (m < 4) m = 4;
+  if (m < 8) m = 8;  // (the survivor count spreads like a Gamma(m) variable: m >= 8 keeps "fewer than kk survive" out of reach)
   if (m > z.S) m = z.S;
   z.m = (int)m;
   return z;
@@ -544,6 +564,17 @@ bool dot_topk_eligible(int64_t N, int R, int K, int kk) {
   const Sizes z = sizes_of(N, kk);
   if ((int64_t)z.cap * 8 > N || z.m > MOL_MAX_K || kk > MOL_MAX_K) return false;
   return true;
+}
+
+int dot_topk_norm_cache(const float* items, int64_t N, int64_t pitch, int col0, int K, float* cache, cudaStream_t st) {
+  if (N == 0) return MOL_OK;
+  int64_t blocks = (N + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  row_norm_max_kernel<<<(unsigned)blocks, 256, 0, st>>>(items, N, pitch, col0, K, cache + 1, cache);
+  MOL_LAUNCH_CHECK();
+  norm_publish_kernel<<<1, 1, 0, st>>>(cache);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
 }
 
 bool dot_topk_aligned(const float* items, int64_t pitch, int col0, const float* Q, int64_t q_pitch) {
@@ -569,7 +600,7 @@ void dot_topk_plan(Arena& a, int64_t N, int R, int K, int kk, float* fb_scores, 
   // the (Rc, S) sample matrix lives in the fallback matrix when that is large enough (it is consumed before any fallback)
   p->samp = ((int64_t)fb_rows * N >= (int64_t)rc * z.S) ? fb_scores : a.take<float>(rc * (size_t)z.S);
   p->samp_aliases_fb = ((int64_t)fb_rows * N >= (int64_t)rc * z.S) ? 1 : 0;
-  const size_t seg = (rc + 2 * 148 + 1) * (size_t)z.m;
+  const size_t seg = rc * 8 * (size_t)z.m;  // the sample select runs on 8 segments per row
   p->seg_scores = a.take<float>(seg);
   p->seg_idx = a.take<int32_t>(seg);
   p->samp_top = a.take<float>(rc * (size_t)z.m);
@@ -581,7 +612,7 @@ void dot_topk_plan(Arena& a, int64_t N, int R, int K, int kk, float* fb_scores, 
   p->cexact = a.take<float>(rc * (size_t)z.cap);
   p->flags = a.take<int32_t>(rc);
   p->any_flag = a.take<int32_t>(rc / (size_t)p->rows_fb + 2);
-  const size_t fseg = (size_t)select_streamed_slots(N, p->rows_fb, kk) * (size_t)kk;
+  const size_t fseg = ((size_t)p->rows_fb + 2 * 148 + 1) * (size_t)kk;  // rows' * select_num_segments(N, rows', kk) slots
   p->fb_seg_scores = a.take<float>(fseg);
   p->fb_seg_idx = a.take<int32_t>(fseg);
   p->xmax = a.take<float>(1);
@@ -601,7 +632,7 @@ int dot_topk_run(const DotTopkPlan& p, const float* items, int64_t pitch, int co
     MOL_CUDA(cudaMemsetAsync(p.xmax, 0, sizeof(float), st));
     int64_t blocks = (N + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    row_norm_max_kernel<<<(unsigned)blocks, 256, 0, st>>>(items, N, pitch, col0, K, p.xmax);
+    row_norm_max_kernel<<<(unsigned)blocks, 256, 0, st>>>(items, N, pitch, col0, K, p.xmax, nullptr);
     MOL_LAUNCH_CHECK();
     xmax_dev = p.xmax;
   }
@@ -618,7 +649,10 @@ int dot_topk_run(const DotTopkPlan& p, const float* items, int64_t pitch, int co
                                 p.samp + (int64_t)c0 * p.S, p.S, nullptr, nullptr, nullptr, nullptr, 0, 0, st));
     }
     {
-      const int S1 = select_num_segments(p.S, rc, m);
+      // (segments of ~4k values: the one-CTA-per-row select of 32k values took 68 us for 512 rows)
+      int S1 = (int)(p.S / 4096);
+      S1 = S1 < 1 ? 1 : (S1 > 8 ? 8 : S1);
+      if ((int64_t)S1 * m > p.S) S1 = 1;
       const float* sel = p.samp;
       const int32_t* pay = nullptr;
       int64_t sn = p.S;
@@ -661,7 +695,7 @@ int dot_topk_run(const DotTopkPlan& p, const float* items, int64_t pitch, int co
       dot_rows_flagged_kernel<<<(unsigned)blocks, 256, (size_t)K * sizeof(float), st>>>(
           items, N, pitch, col0, K, Qc + (int64_t)b1 * q_pitch, q_pitch, nb, fl, p.any_flag + b1 / p.rows_fb, p.fb_scores);
       MOL_LAUNCH_CHECK();
-      const int S2 = select_num_segments_streamed(N, nb, kk);
+      const int S2 = select_num_segments(N, nb, kk);  // (few CTAs: this launch is idle unless a row failed its test)
       const float* sel = p.fb_scores;
       const int32_t* pay = nullptr;
       int64_t sn = N;

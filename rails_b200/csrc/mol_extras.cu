@@ -191,6 +191,13 @@ int mol_dot_scores(const float* items, const float* queries, int64_t num_items, 
 int mol_mips_search(const float* items, const int64_t* item_ids, const float* queries, int64_t num_items,
                     int32_t D, int32_t B, int32_t k, float* out_scores, int64_t* out_ids, void* workspace,
                     size_t workspace_bytes, mol_stream_t stream) {
+  return mol_mips_search_cached(items, item_ids, queries, num_items, D, B, k, nullptr, out_scores, out_ids, workspace,
+                                workspace_bytes, stream);
+}
+
+int mol_mips_search_cached(const float* items, const int64_t* item_ids, const float* queries, int64_t num_items,
+                           int32_t D, int32_t B, int32_t k, float* item_norm_cache, float* out_scores,
+                           int64_t* out_ids, void* workspace, size_t workspace_bytes, mol_stream_t stream) {
   MOL_CHECK_ARG(num_items >= 0 && D >= 1 && B >= 0 && k >= 1 && k <= MOL_MAX_K, "bad arguments");
   MOL_CHECK_ARG(num_items < (1ll << 31) - 256, "num_items must fit int32");
   if (k > num_items) {
@@ -206,9 +213,11 @@ int mol_mips_search(const float* items, const int64_t* item_ids, const float* qu
   MOL_CUDA(cudaMemsetAsync(ws.stats, 0, 8 * sizeof(int32_t), st));
   // streaming path (f4 "fused GEMM + top-k"): tcgen05 tf32 pass + threshold filter + fp32 rescoring of the survivors, no
   // (B, N) matrix - see mol_dotfilter.cuh
-  if (ws.filter && dot_topk_eligible(num_items, B, D, k) && dot_topk_aligned(items, D, 0, queries, D))
-    return dot_topk_run(ws.dp, items, D, 0, D, nullptr, 0.f, queries, D, out_scores, nullptr, out_ids, item_ids, ws.stats,
-                        st);
+  if (ws.filter && dot_topk_eligible(num_items, B, D, k) && dot_topk_aligned(items, D, 0, queries, D)) {
+    if (item_norm_cache) MOL_TRY(dot_topk_norm_cache(items, num_items, D, 0, D, item_norm_cache, st));
+    return dot_topk_run(ws.dp, items, D, 0, D, item_norm_cache, 0.f, queries, D, out_scores, nullptr, out_ids, item_ids,
+                        ws.stats, st);
+  }
   const int64_t rows = ws.rows;
   float* mat = ws.mat;
   char* tk = ws.tk;

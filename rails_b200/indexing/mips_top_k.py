@@ -34,6 +34,7 @@ class MIPSBruteForceTopK(MIPSTopKModule):
         self._ids = None
         self._key = None
         self._ws = None
+        self._norm_cache = None  # {bound on the item norms or -1, accumulator}: mol_mips_search_cached
         if item_embeddings.is_cuda:
             self._sync()
 
@@ -47,6 +48,7 @@ class MIPSBruteForceTopK(MIPSTopKModule):
             self._items = e.squeeze(0).detach().to(torch.float32).contiguous()
             self._ids = i.reshape(-1).detach().to(device=self._items.device, dtype=torch.int64).contiguous()
             self._key = key
+            self._norm_cache = torch.tensor([-1.0, 0.0], dtype=torch.float32, device=self._items.device)
 
     def last_search_stats(self) -> dict:
         """Counters of the last forward(): `filter_strategy` = 1 when the streaming tcgen05 path ran (no (B, N) matrix),
@@ -81,9 +83,9 @@ class MIPSBruteForceTopK(MIPSTopKModule):
             self._ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(
-                lib.mol_mips_search(
+                lib.mol_mips_search_cached(
                     engine._ptr(self._items), engine._ptr(self._ids), engine._ptr(q), N, D, B, int(k),
-                    engine._ptr(out_s), engine._ptr(out_i), engine._ptr(self._ws), self._ws.numel(),
+                    engine._ptr(self._norm_cache), engine._ptr(out_s), engine._ptr(out_i), engine._ptr(self._ws), self._ws.numel(),
                     engine._stream_ptr(dev),
                 )
             )
