@@ -134,6 +134,21 @@ int mol_search(const mol_shape_t* shape, const mol_weights_t* w, const mol_index
                int32_t mode, float* out_scores, int64_t* out_ids, void* workspace,
                size_t workspace_bytes, mol_stream_t stream);
 
+/* The same search with a per-query exclusion list (the seen-item filter of
+ * CandidateIndex.get_top_k_outputs, indexing/candidate_index.py:144-178, moved inside the search): invalid_ids
+ * (B, n_invalid) int64 device; an item whose id is in its query's list never enters the result (ids <= 0 in the list
+ * match nothing when item ids are positive, as in the reference).  out = the top-k over the remaining items - what the
+ * reference obtains by over-fetching k' = k + n_invalid and masking, without the over-fetch.  Needs k + n_invalid <=
+ * min(N, MOL_MAX_K) (MOL_ERR_RANGE / MOL_ERR_INVALID otherwise; callers then over-fetch and call mol_select_valid).
+ * Tensor path: the ids are struck from the survivor buffers of the fused filter (or from the coarse top-K') before the
+ * fp32 rescoring; exact mode and the per-query exact fallback over-fetch internally. */
+int mol_search_excluding_workspace_bytes(const mol_shape_t* shape, int64_t num_items, int32_t B, int32_t k,
+                                         int32_t n_invalid, int32_t mode, size_t* bytes);
+int mol_search_excluding(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
+                         const float* queries, const int64_t* user_ids, int32_t B, int32_t k, int32_t sorted,
+                         int32_t mode, const int64_t* invalid_ids, int32_t n_invalid, float* out_scores,
+                         int64_t* out_ids, void* workspace, size_t workspace_bytes, mol_stream_t stream);
+
 /* Counters of the LAST mol_search / mol_search_host call that used `workspace` (8 x int32, copied to host_stats; this
  * call synchronises the stream): [0] queries re-done by the exact fallback, [1] queries whose candidate filter
  * overflowed, [2] largest survivor count of a query, [3] 1 if the fused-filter strategy ran, [4] 1 if the tensor-core

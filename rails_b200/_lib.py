@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "mol_index_build_workspace_bytes", "mol_index_build", "mol_search_workspace_bytes", "mol_search",
     "mol_search_host", "mol_score_all", "mol_score_all_coarse", "mol_query_prologue", "mol_merge_topk_workspace_bytes",
     "mol_merge_topk", "mol_topk_workspace_bytes", "mol_topk", "mol_launch_count", "mol_launch_count_reset",
-    "mol_profile_enable", "mol_profile_collect", "mol_select_valid", "mol_mips_workspace_bytes", "mol_mips_search", "mol_mips_search_cached",
+    "mol_profile_enable", "mol_profile_collect", "mol_select_valid", "mol_mips_workspace_bytes", "mol_mips_search", "mol_mips_search_cached", "mol_search_excluding_workspace_bytes", "mol_search_excluding",
     "mol_dot_scores", "mol_index_avg_embeddings", "mol_search_avg_workspace_bytes", "mol_search_avg",
     "mol_search_groups_workspace_bytes", "mol_search_groups",
     "mol_weights_prepared_bytes", "mol_weights_prepare", "mol_search_stats",
@@ -157,6 +157,11 @@ def load() -> ctypes.CDLL:
     ]
     lib.mol_weights_prepared_bytes.argtypes = [P(MolShape), P(c_size_t)]
     lib.mol_weights_prepare.argtypes = [P(MolShape), P(MolWeights), c_void_p, c_size_t, c_void_p]
+    lib.mol_search_excluding_workspace_bytes.argtypes = [P(MolShape), c_int64, c_int32, c_int32, c_int32, c_int32, P(c_size_t)]
+    lib.mol_search_excluding.argtypes = [
+        P(MolShape), P(MolWeights), P(MolIndex), c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
+        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
+    ]
     lib.mol_search_stats.argtypes = [c_void_p, P(c_int32), c_void_p]
     lib.mol_pack_topk.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     lib.mol_merge_topk_packed_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, P(c_size_t)]

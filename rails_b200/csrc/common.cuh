@@ -141,6 +141,11 @@ int launch_select_final_i32(const float* scores, const int32_t* payload, int64_t
 int launch_select_final_i64(const float* scores, const int64_t* payload, int64_t n, int64_t ld,
                             int B, int kk, float* out_scores, int64_t* out_ids, cudaStream_t st);
 
+// Seen-item masking + back-fill of a score-sorted (B, kp) list (mol_select_valid); query_flags (optional): only rows with
+// flag != 0 are written.
+int launch_select_valid(const float* scores, const int64_t* ids, const int64_t* invalid_ids, int B, int kp, int n0, int k,
+                        float* out_scores, int64_t* out_ids, const int32_t* query_flags, cudaStream_t st);
+
 int select_num_segments(int64_t n, int B, int kk);
 int select_num_segments_streamed(int64_t n, int B, int kk);
 int64_t select_streamed_slots(int64_t n, int64_t rows, int kk);

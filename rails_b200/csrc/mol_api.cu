@@ -192,6 +192,10 @@ struct SearchWs {
   int samp_stride;      // the sample is every samp_stride-th item tile (1: the first `sample` items)
   int m;                // sample rank that defines the threshold
   int cap;              // survivor capacity per query
+  // per-query exclusion lists (mol_search_excluding): internal over-fetch of the fp32 matrix paths
+  int n0;               // excluded ids per query (0: none)
+  float* ex_scores;     // (chunk, k + n0)
+  int64_t* ex_ids;      // (chunk, k + n0)
   size_t total;
 };
 
@@ -228,7 +232,7 @@ static int64_t filter_min_pairs() {
 }
 
 static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, void* base,
-                       size_t cap, SearchWs* ws) {
+                       size_t cap, SearchWs* ws, int n0 = 0) {
   Dims D = dims_of(s);
   Arena a(base, cap);
   const bool tensor = use_tensor(s, mode);
@@ -254,6 +258,15 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
   ws->cap = 4 * ws->Kp < 4096 ? 4096 : 4 * ws->Kp;
   ws->filter = (tensor && N >= kFilterMinItems && (int64_t)ws->cap * 16 <= N && (int64_t)B * N >= filter_min_pairs()) ? 1 : 0;
   const int64_t n_rows = N > 0 ? N : 1;
+  const int kx = k + n0;  // what the fp32 matrix paths select when ids are excluded (internal over-fetch)
+  if (n0 > 0 && tensor && !ws->filter) {
+    // matrix strategy: the excluded ids are struck from the coarse top-K', so K' grows by the list length (the filter
+    // strategy strikes them from the survivor buffers, before the K' best are chosen)
+    int64_t kp = (int64_t)ws->Kp + n0;
+    if (kp > MOL_MAX_K) kp = MOL_MAX_K;
+    if (kp > N) kp = N;
+    ws->Kp = (int)kp;
+  }
   if (ws->filter) {
     const int64_t target = ws->cap / 4;
     int64_t sample = 32 * N / target;  // -> threshold rank m >= 32 in the sample
@@ -280,7 +293,7 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
     if ((size_t)ws->chunk_fb * (size_t)n_rows > n_scores) n_scores = (size_t)ws->chunk_fb * (size_t)n_rows;
     ws->scores = a.take<float>(n_scores);
     // segment survivors of any (rows <= chunk, kk <= max(m, k)) select: rows * S(rows) < rows + 2 * 148 + 1
-    const int kk_max = ws->m > k ? ws->m : k;
+    const int kk_max = ws->m > kx ? ws->m : kx;
     const size_t seg = (size_t)(ws->chunk + 2 * 148 + 1) * kk_max;
     ws->S = 0;
     ws->seg_scores = a.take<float>(seg);
@@ -304,7 +317,7 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
     ws->m = 0;
     ws->S = 0;
     ws->scores = a.take<float>((size_t)chunk * (size_t)N);
-    const size_t seg = (size_t)(chunk + 2 * 148 + 1) * (ws->Kp > k ? ws->Kp : k);
+    const size_t seg = (size_t)(chunk + 2 * 148 + 1) * (ws->Kp > kx ? ws->Kp : kx);
     ws->seg_scores = a.take<float>(seg);
     ws->seg_idx = a.take<int32_t>(seg);
     ws->samp_top = nullptr;
@@ -318,6 +331,13 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
     const int64_t max_rows = tiles > 0 ? ((1ll << 31) - 1) / tiles : ws->chunk;
     if (ws->chunk > max_rows) ws->chunk = (int)(max_rows < 1 ? 1 : max_rows);
     if (ws->chunk_fb > ws->chunk) ws->chunk_fb = ws->chunk;
+  }
+  ws->n0 = n0;
+  ws->ex_scores = nullptr;
+  ws->ex_ids = nullptr;
+  if (n0 > 0) {
+    ws->ex_scores = a.take<float>((size_t)ws->chunk * (size_t)(k + n0));
+    ws->ex_ids = a.take<int64_t>((size_t)ws->chunk * (size_t)(k + n0));
   }
   ws->cand_scores = a.take<float>((size_t)ws->chunk * ws->Kp);
   ws->cand_idx = a.take<int32_t>((size_t)ws->chunk * ws->Kp);
@@ -370,11 +390,56 @@ static int topk_of_matrix(const SearchWs& ws, const float* scores, int64_t n, in
                                  id_map, flags, st);
 }
 
+// Strikes the excluded ids from candidate lists: idx (bc, n) int32 item positions (< 0 = empty slot); an entry whose id
+// (item_ids[position], or the position itself) is in the query's list invalid (bc, n0) becomes -1 - the rescoring gives
+// it -inf and the selects skip it.  One block per query, the list in shared memory.
+__global__ void __launch_bounds__(256)
+exclude_candidates_kernel(int32_t* __restrict__ idx, int64_t n, const int32_t* __restrict__ cnt,
+                          const int64_t* __restrict__ item_ids, const int64_t* __restrict__ invalid, int n0) {
+  extern __shared__ int64_t ex_inv[];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < n0; i += blockDim.x) ex_inv[i] = invalid[(int64_t)b * n0 + i];
+  __syncthreads();
+  int64_t used = n;
+  if (cnt) used = cnt[b] < n ? cnt[b] : n;
+  int32_t* row = idx + (int64_t)b * n;
+  for (int64_t j = threadIdx.x; j < used; j += blockDim.x) {
+    const int32_t p = row[j];
+    if (p < 0) continue;
+    const int64_t id = item_ids ? item_ids[p] : (int64_t)p;
+    bool hit = false;
+    for (int i = 0; i < n0; ++i) hit |= (ex_inv[i] == id);
+    if (hit) row[j] = -1;
+  }
+}
+static int exclude_candidates(int32_t* idx, int64_t n, const int32_t* cnt, int bc, const int64_t* item_ids,
+                              const int64_t* invalid, int n0, cudaStream_t st) {
+  if (bc == 0 || n0 == 0) return MOL_OK;
+  const size_t smem = (size_t)n0 * sizeof(int64_t);
+  if (smem > 48 * 1024)
+    MOL_CUDA(cudaFuncSetAttribute(exclude_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  exclude_candidates_kernel<<<bc, 256, smem, st>>>(idx, n, cnt, item_ids, invalid, n0);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
+// top-k of an exact (bc, N) score matrix; with an exclusion list: the top-(k + n0) and, from that, the first k entries
+// whose id is not excluded (launch_select_valid: the masking of indexing/candidate_index.py:155-178)
+static int exact_topk(const SearchWs& ws, const mol_index_t& ix, int bc, int k, const int64_t* invalid, float* o_scores,
+                      int64_t* o_ids, const int32_t* flags, cudaStream_t st) {
+  const int64_t N = ix.num_items;
+  if (ws.n0 == 0)
+    return topk_of_matrix(ws, ws.scores, N, N, bc, k, o_scores, nullptr, o_ids, ix.item_ids, flags, st);
+  const int kx = k + ws.n0;
+  MOL_TRY(topk_of_matrix(ws, ws.scores, N, N, bc, kx, ws.ex_scores, nullptr, ws.ex_ids, ix.item_ids, flags, st));
+  return launch_select_valid(ws.ex_scores, ws.ex_ids, invalid, bc, kx, ws.n0, k, o_scores, o_ids, flags, st);
+}
+
 // Flagged queries are re-done exactly, in sub-chunks whose (rows, N) fp32 matrix fits the workspace (kernels
 // exit immediately for unflagged rows).
 static int exact_fallback(const mol_shape_t& s, const mol_weights_t& w, const mol_index_t& ix, const SearchWs& ws,
-                          const Prepared& prep, const float* qsub, const float* gq, int bc, int k, float* o_scores,
-                          int64_t* o_ids, cudaStream_t st) {
+                          const Prepared& prep, const float* qsub, const float* gq, int bc, int k, const int64_t* invalid,
+                          float* o_scores, int64_t* o_ids, cudaStream_t st) {
   Dims D = dims_of(s);
   const int64_t N = ix.num_items;
   for (int b1 = 0; b1 < bc; b1 += ws.chunk_fb) {
@@ -382,8 +447,8 @@ static int exact_fallback(const mol_shape_t& s, const mol_weights_t& w, const mo
     const int32_t* fl = ws.flags + b1;
     MOL_TRY(launch_exact_scores(s, w, ix, prep.w1t, prep.w2t, qsub + (size_t)b1 * D.Pq * D.d, gq + (size_t)b1 * D.L, nb,
                                 nullptr, N, N, ws.scores, fl, st));
-    MOL_TRY(topk_of_matrix(ws, ws.scores, N, N, nb, k, o_scores + (size_t)b1 * k, nullptr, o_ids + (size_t)b1 * k,
-                           ix.item_ids, fl, st));
+    MOL_TRY(exact_topk(ws, ix, nb, k, invalid ? invalid + (size_t)b1 * ws.n0 : nullptr, o_scores + (size_t)b1 * k,
+                       o_ids + (size_t)b1 * k, fl, st));
   }
   return MOL_OK;
 }
@@ -401,7 +466,8 @@ __global__ void stats_init_kernel(int32_t* stats, int filter, int tensor, int kp
 
 static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_index_t& ix,
                        const float* queries, const int64_t* user_ids, int B, int k, int mode,
-                       float* out_scores, int64_t* out_ids, const SearchWs& ws_in, cudaStream_t st) {
+                       float* out_scores, int64_t* out_ids, const SearchWs& ws_in, cudaStream_t st,
+                       const int64_t* invalid_ids = nullptr) {
   Dims D = dims_of(s);
   const int64_t N = ix.num_items;
   const bool tensor = use_tensor(s, mode);
@@ -425,12 +491,13 @@ static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_i
     const float* gq = ws.gq + (size_t)b0 * D.L;
     float* o_scores = out_scores + (size_t)b0 * k;
     int64_t* o_ids = out_ids + (size_t)b0 * k;
+    const int64_t* invalid = (ws.n0 > 0 && invalid_ids) ? invalid_ids + (size_t)b0 * ws.n0 : nullptr;
     if (!tensor) {
       NvtxRange r("mol:exact");
       prof_begin(st);
       MOL_TRY(launch_exact_scores(s, w, ix, prep.w1t, prep.w2t, qsub, gq, bc, nullptr, N, N, ws.scores, nullptr, st));
       prof_end(st);
-      MOL_TRY(topk_of_matrix(ws, ws.scores, N, N, bc, k, o_scores, nullptr, o_ids, ix.item_ids, nullptr, st));
+      MOL_TRY(exact_topk(ws, ix, bc, k, invalid, o_scores, o_ids, nullptr, st));
       continue;
     }
     const int kk = ws.Kp;
@@ -446,6 +513,7 @@ static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_i
       }
       NvtxRange r("mol:select");
       MOL_TRY(topk_of_matrix(ws, ws.scores, N, N, bc, kk, ws.cand_scores, ws.cand_idx, nullptr, nullptr, nullptr, st));
+      if (invalid) MOL_TRY(exclude_candidates(ws.cand_idx, kk, nullptr, bc, ix.item_ids, invalid, ws.n0, st));
     } else {
       // filter strategy.  (1) threshold pass over a strided sample of the item tiles
       const int sample_tiles = (int)(ws.sample / 128);
@@ -492,8 +560,9 @@ static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_i
         MOL_TRY(coarse_run(s, ix, ws.coarse, bc, o2, st));
         prof_end(st);
       }
-      // (3) the K' best survivors per query
+      // (3) the K' best survivors per query (excluded ids struck first: they never take one of the K' places)
       NvtxRange r("mol:select");
+      if (invalid) MOL_TRY(exclude_candidates(ws.fidx, ws.cap, ws.fcnt, bc, ix.item_ids, invalid, ws.n0, st));
       MOL_TRY(launch_select_final_i32(ws.fscores, ws.fidx, ws.cap, ws.cap, bc, kk, ws.cand_scores, ws.cand_idx,
                                       nullptr, nullptr, nullptr, st));
     }
@@ -507,7 +576,7 @@ static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_i
       MOL_TRY(coarse_safety_flags(ws.cand_scores, ws.exact_scores, o_scores, bc, kk, k, ws.coarse.overflow,
                                   ix.half_overflow, ws.filter ? ws.fcnt : nullptr, thr, ws.m, ws.cap, ws.flags,
                                   ws.stats, st));
-      MOL_TRY(exact_fallback(s, w, ix, ws, prep, qsub, gq, bc, k, o_scores, o_ids, st));
+      MOL_TRY(exact_fallback(s, w, ix, ws, prep, qsub, gq, bc, k, invalid, o_scores, o_ids, st));
     }
   }
   return MOL_OK;
@@ -698,6 +767,39 @@ int mol_search(const mol_shape_t* shape, const mol_weights_t* w, const mol_index
   MOL_TRY(plan_search(*shape, index->num_items, B, k, mode, workspace, workspace_bytes, &ws));
   return search_impl(*shape, *w, *index, queries, user_ids, B, k, mode, out_scores, out_ids, ws,
                      static_cast<cudaStream_t>(stream));
+}
+
+int mol_search_excluding_workspace_bytes(const mol_shape_t* shape, int64_t num_items, int32_t B, int32_t k,
+                                         int32_t n_invalid, int32_t mode, size_t* bytes) {
+  MOL_TRY(check_shape(shape));
+  MOL_CHECK_ARG(bytes && B >= 0 && k >= 0 && num_items >= 0 && n_invalid >= 0, "bad arguments");
+  MOL_CHECK_ARG(mode != MOL_MODE_TENSOR || coarse_supported(*shape), "shape not supported by the tensor-core path");
+  SearchWs ws;
+  MOL_TRY(plan_search(*shape, num_items, B > 0 ? B : 1, k > 0 ? k : 1, mode, nullptr, 0, &ws, n_invalid));
+  *bytes = ws.total + 256;
+  return MOL_OK;
+}
+
+int mol_search_excluding(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,
+                         const float* queries, const int64_t* user_ids, int32_t B, int32_t k, int32_t sorted,
+                         int32_t mode, const int64_t* invalid_ids, int32_t n_invalid, float* out_scores,
+                         int64_t* out_ids, void* workspace, size_t workspace_bytes, mol_stream_t stream) {
+  (void)sorted;
+  MOL_TRY(check_search_args(shape, w, index, queries, user_ids, B, k, mode, out_scores, out_ids));
+  MOL_CHECK_ARG(n_invalid >= 0 && (n_invalid == 0 || invalid_ids || B == 0), "exclusion list missing");
+  MOL_CHECK_ARG((int64_t)k + n_invalid <= MOL_MAX_K, "k + n_invalid = %lld exceeds MOL_MAX_K=%d", (long long)k + n_invalid,
+                MOL_MAX_K);
+  if ((int64_t)k + n_invalid > index->num_items) {
+    set_error("selected index k out of range (k + n_invalid = %lld > %lld items)", (long long)k + n_invalid,
+              (long long)index->num_items);
+    return MOL_ERR_RANGE;
+  }
+  if (B == 0) return MOL_OK;
+  MOL_CHECK_ARG(workspace, "workspace is NULL");
+  SearchWs ws;
+  MOL_TRY(plan_search(*shape, index->num_items, B, k, mode, workspace, workspace_bytes, &ws, n_invalid));
+  return search_impl(*shape, *w, *index, queries, user_ids, B, k, mode, out_scores, out_ids, ws,
+                     static_cast<cudaStream_t>(stream), n_invalid > 0 ? invalid_ids : nullptr);
 }
 
 int mol_search_host(const mol_shape_t* shape, const mol_weights_t* w, const mol_index_t* index,

@@ -18,13 +18,14 @@ constexpr int SV_THREADS = 256;
 __global__ void __launch_bounds__(SV_THREADS)
 select_valid_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids,
                     const int64_t* __restrict__ invalid, int kp, int n0, int k, float* __restrict__ out_scores,
-                    int64_t* __restrict__ out_ids) {
+                    int64_t* __restrict__ out_ids, const int32_t* __restrict__ query_flags) {
   extern __shared__ int64_t sv_smem[];
   int64_t* inv = sv_smem;                                   // n0
   unsigned char* seen = reinterpret_cast<unsigned char*>(inv + n0);  // kp
   __shared__ int part[SV_THREADS];
   __shared__ int totals[2];
   const int b = blockIdx.x, tid = threadIdx.x;
+  if (query_flags && query_flags[b] == 0) return;
   const int64_t* row_ids = ids + (int64_t)b * kp;
   for (int i = tid; i < n0; i += SV_THREADS) inv[i] = invalid[(int64_t)b * n0 + i];
   __syncthreads();
@@ -108,6 +109,18 @@ select_valid_kernel(const float* __restrict__ scores, const int64_t* __restrict_
   }
 }
 
+int launch_select_valid(const float* scores, const int64_t* ids, const int64_t* invalid_ids, int B, int kp, int n0, int k,
+                        float* out_scores, int64_t* out_ids, const int32_t* query_flags, cudaStream_t st) {
+  if (B == 0) return MOL_OK;
+  const size_t smem = (size_t)n0 * sizeof(int64_t) + (size_t)kp + 16;
+  MOL_CHECK_ARG(smem <= 200 * 1024, "k' + invalid list too large for one block (%zu bytes)", smem);
+  if (smem > 48 * 1024)
+    MOL_CUDA(cudaFuncSetAttribute(select_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  select_valid_kernel<<<B, SV_THREADS, smem, st>>>(scores, ids, invalid_ids, kp, n0, k, out_scores, out_ids, query_flags);
+  MOL_LAUNCH_CHECK();
+  return MOL_OK;
+}
+
 }  // namespace mol
 
 using namespace mol;
@@ -120,14 +133,8 @@ int mol_select_valid(const float* scores, const int64_t* ids, const int64_t* inv
   MOL_CHECK_ARG(B >= 0 && k >= 1 && k_prime >= k && n_invalid >= 0, "bad arguments (need k' >= k >= 1)");
   if (B == 0) return MOL_OK;
   MOL_CHECK_ARG(scores && ids && out_scores && out_ids && (n_invalid == 0 || invalid_ids), "NULL buffer");
-  const size_t smem = (size_t)n_invalid * sizeof(int64_t) + (size_t)k_prime + 16;
-  MOL_CHECK_ARG(smem <= 200 * 1024, "k' + invalid list too large for one block (%zu bytes)", smem);
-  if (smem > 48 * 1024)
-    MOL_CUDA(cudaFuncSetAttribute(select_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  select_valid_kernel<<<B, SV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      scores, ids, invalid_ids, k_prime, n_invalid, k, out_scores, out_ids);
-  MOL_LAUNCH_CHECK();
-  return MOL_OK;
+  return launch_select_valid(scores, ids, invalid_ids, B, k_prime, n_invalid, k, out_scores, out_ids, nullptr,
+                             static_cast<cudaStream_t>(stream));
 }
 
 namespace {

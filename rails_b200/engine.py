@@ -172,8 +172,10 @@ def search(
     k: int,
     sorted: bool = True,
     mode: int = _lib.MODE_AUTO,
+    invalid_ids: Optional[torch.Tensor] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """mol_search with device buffers.  Returns (scores (B,k) fp32, ids (B,k) int64)."""
+    """mol_search with device buffers.  Returns (scores (B,k) fp32, ids (B,k) int64).  invalid_ids (B, N0) int64: ids
+    excluded per query inside the search (mol_search_excluding; needs k + N0 <= N)."""
     lib = _lib.load()
     _require_cuda(queries, "query_embeddings")
     dev = index.device
@@ -187,6 +189,22 @@ def search(
     out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
     nbytes = c_size_t()
+    if invalid_ids is not None and invalid_ids.size(1) > 0:
+        inv = invalid_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
+        if inv.size(0) != B:
+            raise ValueError(f"invalid_ids has {inv.size(0)} rows for {B} queries")
+        n0 = int(inv.size(1))
+        _lib.check(lib.mol_search_excluding_workspace_bytes(byref(weights.shape), index.N, B, k, n0, mode, byref(nbytes)))
+        ws = workspace.get(nbytes.value)
+        with torch.cuda.device(dev):
+            _lib.check(
+                lib.mol_search_excluding(
+                    byref(weights.shape), byref(weights.struct), byref(index.struct), _ptr(q), _ptr(uid), B, k,
+                    1 if sorted else 0, mode, _ptr(inv), n0, _ptr(out_s), _ptr(out_i), _ptr(ws), ws.numel(),
+                    _stream_ptr(dev),
+                )
+            )
+        return out_s, out_i
     _lib.check(lib.mol_search_workspace_bytes(byref(weights.shape), index.N, B, k, mode, byref(nbytes)))
     ws = workspace.get(nbytes.value)
     with torch.cuda.device(dev):

@@ -28,8 +28,11 @@ class TopKModule(torch.nn.Module):
 class CandidateIndex(object):
     """Mirror of the reference's eval-side `CandidateIndex` (indexing/candidate_index.py:31-185), restricted to what
     the brute-force eval path uses: `ids`, `embeddings`, `num_objects` and `get_top_k_outputs`.  The seen-item
-    masking + back-fill (:155-178) runs in one CUDA kernel (`mol_select_valid`) — no boolean (B, k', N0) tensor and
-    no `torch.nonzero` host sync.  SURVEY.md §8 row f2."""
+    masking + back-fill (:155-178) never materialises a boolean (B, k', N0) tensor and never syncs the host
+    (`torch.nonzero`).  With a top-k module that takes the exclusion list itself (`supports_invalid_ids`,
+    MoLBruteForceTopK) and k + N0 <= X, the seen ids are excluded INSIDE the search (`mol_search_excluding`): no k' = k + N0
+    over-fetch, the result is the top-k over the unseen items directly.  Otherwise the over-fetched list goes through
+    one CUDA kernel (`mol_select_valid`).  SURVEY.md §8 row f2."""
 
     def __init__(self, ids: torch.Tensor, embeddings: torch.Tensor, invalid_ids=None, debug_path=None) -> None:
         super().__init__()
@@ -70,6 +73,17 @@ class CandidateIndex(object):
         if return_embeddings:
             raise NotImplementedError("return_embeddings=True is broken in the reference (:182) and not implemented")
         max_num_invalid_ids = 0 if invalid_ids is None else invalid_ids.size(1)
+        if (
+            max_num_invalid_ids > 0
+            and truncate_k_prime_to is None
+            and getattr(top_k_module, "supports_invalid_ids", False)
+            and k + max_num_invalid_ids <= min(self.num_objects, _lib.MOL_MAX_K)
+            and query_embeddings.is_cuda
+        ):
+            # at most N0 of the best k + N0 items are excluded, so "the first k unseen entries of the top-(k + N0)" (the
+            # reference's result, :155-178, no back-fill needed) IS the top-k over the unseen items
+            scores, ids = top_k_module(query_embeddings=query_embeddings, k=k, invalid_ids=invalid_ids, **aux_payloads)
+            return ids, scores, None
         k_prime = min(k + max_num_invalid_ids, self.num_objects)
         if truncate_k_prime_to is not None:
             k_prime = min(k_prime, truncate_k_prime_to)

@@ -72,6 +72,8 @@ class MoLTopKModule(TopKModule):
 
 
 class MoLBruteForceTopK(MoLTopKModule):
+    supports_invalid_ids = True  # forward(..., invalid_ids=(B, N0)) excludes ids inside the search
+
     def __init__(
         self,
         mol_module: MoLSimilarity,
@@ -118,14 +120,18 @@ class MoLBruteForceTopK(MoLTopKModule):
                 indexing/candidate_index.py:149 of the reference).
             sorted: bool. Results are always returned sorted (descending), which satisfies both values.
             **kwargs: "user_ids" is consumed when uid embeddings are configured; "timestamps" / "ratings"
-                (data/eval.py:148) are accepted and ignored.
+                (data/eval.py:148) are accepted and ignored.  "invalid_ids" ((B, N0) int64, an extension used by
+                CandidateIndex.get_top_k_outputs): ids excluded per query INSIDE the search - the result is the top-k
+                over the other items, which is what the reference gets from its k + N0 over-fetch and masking
+                (indexing/candidate_index.py:144-178) whenever k + N0 <= X.
         Returns:
             Tuple of (top_k_scores x float, top_k_ids x int64), both of shape (B, K,)
         """
         index = self._ensure_index()
         dev = index.device
         weights = self._mol_module.packed_weights(dev)
-        if self._cuda_graph and query_embeddings.size(0) > 0:
+        invalid_ids = kwargs.get("invalid_ids")
+        if self._cuda_graph and query_embeddings.size(0) > 0 and invalid_ids is None:
             uid = kwargs.get("user_ids")
             key = (int(query_embeddings.size(0)), int(k), id(index), id(weights))
             g = self._graphs.get(key)
@@ -141,7 +147,7 @@ class MoLBruteForceTopK(MoLTopKModule):
         self._last_workspace = self._mol_module.workspace(dev)
         scores, ids = engine.search(
             weights, index, self._mol_module.workspace(dev), query_embeddings, kwargs.get("user_ids"), int(k), sorted,
-            self._mode,
+            self._mode, invalid_ids,
         )
         return scores.to(query_embeddings.dtype), ids
 

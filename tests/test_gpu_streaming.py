@@ -123,3 +123,38 @@ def test_approximate_modules_streaming_equals_materialised(cfg, N, B, monkeypatc
         assert st["filter_overflows"] == 0, st
         assert torch.equal(out[True][1], out[False][1]), type(top).__name__
         assert torch.equal(out[True][0], out[False][0]), type(top).__name__
+
+
+@pytest.mark.parametrize("mode_name,N,force_filter", [("auto", 150_000, True), ("auto", 20_000, False), ("exact", 20_000, False)])
+def test_in_search_exclusion_equals_overfetch_and_mask(mode_name, N, force_filter, monkeypatch):
+    """seen ids excluded INSIDE the search (mol_search_excluding) must give exactly what the
+    reference's recipe gives (indexing/candidate_index.py:144-178: over-fetch k' = k + N0, mask, keep the first k) - here
+    the over-fetch + mol_select_valid path, itself pinned to the oracle in test_gpu_parity.py."""
+    from rails_b200 import _lib
+    from rails_b200.indexing.candidate_index import CandidateIndex
+    from rails_b200.indexing.mol_top_k import MoLBruteForceTopK
+
+    if force_filter:
+        monkeypatch.setenv("MOL_B200_FILTER_MIN_PAIRS", "0")
+    cfg = CFG_8x8x32
+    B, k, n0 = 9, 50, 37
+    mol, _ = build_module(cfg, None, DEV, seed=31)
+    items, ids, q, _ = synthetic_inputs(cfg, N, B, 31, DEV)
+    mode = _lib.MODE_EXACT if mode_name == "exact" else _lib.MODE_AUTO
+    top = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=mode)
+    _, best = top(q, k=k + n0)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    # the list of a query: 20 of its own best items (ranks 0, 2, 4, ...), random ids, duplicates and zero padding
+    inv = torch.cat(
+        [best[:, 0:40:2], torch.randint(1, N + 1, (B, n0 - 25), device=DEV, generator=g), best[:, 0:2],
+         torch.zeros((B, 3), dtype=torch.int64, device=DEV)], dim=1)
+    assert inv.size(1) == n0
+    index = CandidateIndex(ids=ids.unsqueeze(0), embeddings=items.unsqueeze(0))
+    got_i, got_s, _ = index.get_top_k_outputs(q, k, {}, top, inv)
+    st = top.last_search_stats()
+    ref_i, ref_s, _ = index.get_top_k_outputs(q, k, {}, top, inv, truncate_k_prime_to=k + n0)  # over-fetch + mask
+    assert st["filter_strategy"] == (1 if force_filter else 0) and st["fallback_queries"] == 0, st
+    assert torch.equal(got_i, ref_i)
+    assert torch.equal(got_s, ref_s)
+    for b in range(B):
+        assert not set(got_i[b].tolist()) & set(inv[b].tolist())
