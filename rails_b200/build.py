@@ -23,7 +23,7 @@ LIB = os.path.join(OUT_DIR, "libmol_b200.so")
 PROBE = os.path.join(OUT_DIR, "libmol_probe.so")
 
 SOURCES = ["mol_api.cu", "mol_prologue.cu", "mol_exact.cu", "mol_select.cu", "mol_coarse_sm100.cu", "mol_extras.cu",
-           "mol_dotfilter_sm100.cu"]
+           "mol_dotfilter_sm100.cu", "mol_linear_x3_sm100.cu"]
 PROBE_SOURCES = ["probe_sm100.cu"]
 
 NVCC_FLAGS = [

@@ -146,6 +146,13 @@ int launch_select_final_i64(const float* scores, const int64_t* payload, int64_t
 int launch_select_valid(const float* scores, const int64_t* ids, const int64_t* invalid_ids, int B, int kp, int n0, int k,
                         float* out_scores, int64_t* out_ids, const int32_t* query_flags, cudaStream_t st);
 
+// Index build on the tensor cores (mol_linear_x3_sm100.cu): tf32 x 3 split GEMMs with the l2-norm / silu / fp16-image
+// epilogues fused; `supported` looks at the shape, the corpus size and the alignment of raw_items
+// (MOL_B200_INDEX_X3=0 keeps the CUDA-core build).
+bool index_build_x3_supported(const mol_shape_t& s, const mol_index_t& ix);
+size_t index_build_x3_workspace_bytes(const mol_shape_t& s, int64_t N);
+int index_build_x3(const mol_shape_t& s, const mol_weights_t& w, const mol_index_t& ix, void* workspace, cudaStream_t st);
+
 int select_num_segments(int64_t n, int B, int kk);
 int select_num_segments_streamed(int64_t n, int B, int kk);
 int64_t select_streamed_slots(int64_t n, int64_t rows, int kk);

@@ -688,6 +688,8 @@ int mol_index_build_workspace_bytes(const mol_shape_t* shape, int64_t num_items,
   Dims D = dims_of(*shape);
   int cols = D.Px * D.d > D.Hgi ? D.Px * D.d : D.Hgi;
   *bytes = align_up((size_t)num_items * cols * sizeof(float), 256) + 256;
+  const size_t x3 = index_build_x3_workspace_bytes(*shape, num_items);  // (the tensor-core build needs less: the max)
+  if (x3 > *bytes) *bytes = x3;
   return MOL_OK;
 }
 
@@ -705,6 +707,8 @@ int mol_index_build(const mol_shape_t* shape, const mol_weights_t* w, const mol_
     set_error("index build workspace too small: need %zu, got %zu", need, workspace_bytes);
     return MOL_ERR_WORKSPACE;
   }
+  // tensor-core build: tf32 x 3 split GEMMs with fused l2-norm / silu / fp16-image epilogues (mol_linear_x3_sm100.cu)
+  if (N > 0 && index_build_x3_supported(*shape, *index)) return index_build_x3(*shape, *w, *index, workspace, st);
   float* tmp = static_cast<float*>(workspace);
   const int64_t Np = pad128(N);
   // zero the fp16 pad rows (and everything else) so the tensor-core pass can read whole tiles

@@ -9,7 +9,7 @@ result tie-aware."""
 import pytest
 import torch
 
-from tests.helpers import CFG_8x8x32, CFG_8x4x128, build_module, synthetic_inputs
+from tests.helpers import CFG_8x8x32, CFG_8x4x128, CFG_16x16x64, build_module, synthetic_inputs
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -158,3 +158,56 @@ def test_in_search_exclusion_equals_overfetch_and_mask(mode_name, N, force_filte
     assert torch.equal(got_s, ref_s)
     for b in range(B):
         assert not set(got_i[b].tolist()) & set(inv[b].tolist())
+
+
+def _index_arrays(ix):
+    """fp32 and fp16 caches of an engine.IndexHandle as tensors (copies)."""
+    s = ix.weights.shape
+    N, nx, L = ix.N, s.item_dot_product_groups * s.dot_product_dimension, s.query_dot_product_groups * s.item_dot_product_groups
+    Np = (N + 127) // 128 * 128
+    base = ix.blob.data_ptr()
+
+    def view(ptr, count, dtype, width):
+        off = ptr - base
+        return ix.blob[off : off + count * width].view(dtype).clone()
+
+    return {
+        "xsub_f32": view(ix.struct.xsub_f32, N * nx, torch.float32, 4).view(N, nx),
+        "gi_f32": view(ix.struct.gi_f32, N * L, torch.float32, 4).view(N, L),
+        "xsub_half": view(ix.struct.xsub_half, Np * nx, torch.float16, 2).view(Np, nx),
+        "gi_half": view(ix.struct.gi_half, Np * L, torch.float16, 2).view(Np, L),
+    }
+
+
+@pytest.mark.parametrize("cfg,N", [(CFG_8x8x32, 100_000 + 37), (CFG_16x16x64, 20_000 + 1)])
+def test_tensor_core_index_build_matches_cuda_core_build(cfg, N, monkeypatch):
+    """the tf32 x 3 tensor-core index build (fused l2-norm / silu / fp16 image epilogues) against
+    the fp32 CUDA-core build and against the CPU oracle's item side (item_embeddings_fns.py:165-182,
+    similarity_fn.py:170-171).  fp32 caches: within fp32 rounding noise; fp16 copies: at most one fp16 ulp apart; the
+    pad rows of the fp16 copies are zero."""
+    from oracle import mol_oracle as O
+    from rails_b200 import engine
+
+    mol, _ = build_module(cfg, None, DEV, seed=41)
+    items, ids, _, _ = synthetic_inputs(cfg, N, 1, 41, DEV)
+    w = mol.packed_weights(torch.device(DEV))
+    out = {}
+    for x3 in ("1", "0"):
+        monkeypatch.setenv("MOL_B200_INDEX_X3", x3)
+        ix = engine.IndexHandle(w, items, ids)
+        torch.cuda.synchronize()
+        out[x3] = _index_arrays(ix)
+    a, b = out["1"], out["0"]
+    assert (a["xsub_f32"] - b["xsub_f32"]).abs().max().item() < 2e-6       # unit vectors
+    gscale = b["gi_f32"].abs().max().item()
+    assert (a["gi_f32"] - b["gi_f32"]).abs().max().item() < 2e-6 * max(gscale, 1.0)
+    assert (a["xsub_half"].float() - b["xsub_half"].float()).abs().max().item() <= 2 ** -11 + 1e-7   # one fp16 ulp below 1
+    assert (a["gi_half"].float() - b["gi_half"].float()).abs().max().item() <= 2 ** -10 * max(gscale, 1.0)
+    assert bool((a["xsub_half"][N:] == 0).all()) and bool((a["gi_half"][N:] == 0).all())
+    # oracle item side on a slice
+    sd = {k_: v.detach().cpu() for k_, v in mol.state_dict().items()}
+    sl = slice(N - 3000, N)
+    xs_ref = O.item_sub_embeddings(cfg, sd, items[sl].cpu())
+    gi_ref = O._mlp_silu(items[sl].cpu(), sd[O.K_GI_W1], sd[O.K_GI_B1], sd[O.K_GI_W2])
+    assert (a["xsub_f32"][sl].cpu() - xs_ref.reshape(3000, -1)).abs().max().item() < 5e-6
+    assert (a["gi_f32"][sl].cpu() - gi_ref).abs().max().item() < 5e-6 * max(gscale, 1.0)
