@@ -7,13 +7,13 @@
 // ~2^-22 relative, the size of the rounding noise of an fp32 fmaf chain of the same length).  The exact caches
 // (xsub_f32 / gi_f32) therefore agree with the CUDA-core build to ~1e-6 and every parity bound on the scores holds.
 //
-// One persistent CTA per SM, 448 threads:
+// One persistent CTA per SM, 512 threads (setmaxnreg: 72 registers for the control warps, 184 for the epilogue warps):
 //   warp 0        TMA producer: W_hi / W_lo of this launch once (K / 32 boxes of nc rows each), then the A tiles (128 rows)
 //                 box by box into a ring of raw fp32 stages;
 //   warp 1        MMA issuer: per box 4 K steps x 3 MMAs into one of two 256-column TMEM accumulators;
 //   warps 2..5    splitter: raw box -> (hi, lo) boxes.  The split is elementwise and written at the same offsets, so the
 //                 128-byte swizzle of the TMA box is preserved without knowing it;
-//   warps 6..13   epilogue (two warps per TMEM lane quarter, each half of the columns), TMEM lane = row:
+//   warps 8..15   epilogue (two warps per TMEM lane quarter, each half of the columns), TMEM lane = row:
 //                   PROJ  + bias, l2-norm over groups of d columns, fp32 row and fp16 row (pad rows: zeros);
 //                   SILU  + bias, v / (1 + exp(-v)), fp32 row (the hidden layer of the gating MLP);
 //                   GI    columns [0, L): fp32 row; columns [L, 2L) (the same weights with rows permuted into the coarse
@@ -34,12 +34,18 @@ namespace {
 
 constexpr int LX_TILE = 128;
 constexpr int LX_SPLIT_WARPS = 4, LX_EPI_WARPS = 8;
-constexpr int LX_THREADS = 64 + 32 * (LX_SPLIT_WARPS + LX_EPI_WARPS);  // 448
+// 16 warps = 4 warpgroups: {producer, MMA issuer, splitter x 2}, {splitter x 2, 2 idle}, {epilogue x 4}, {epilogue x 4};
+// setmaxnreg moves the registers of the first two (72 each) to the epilogue warps (184 each)
+constexpr int LX_THREADS = 512;
+constexpr int LX_CTL_REGS = 72, LX_EPI_REGS = 184;
+static_assert(256 * LX_CTL_REGS + 256 * LX_EPI_REGS <= 65536, "register pool over-committed");
 constexpr int LX_EPI_THREADS = 32 * LX_EPI_WARPS;
-constexpr int LX_EPI_WARP0 = 2 + LX_SPLIT_WARPS;
-constexpr int LX_RAW_STAGES = 2, LX_SPLIT_STAGES = 2;
+constexpr int LX_EPI_WARP0 = 8;
+constexpr int LX_MAX_RAW = 6, LX_MAX_SPLIT = 2;  // pipeline stages (how many fit is decided per launch)
 constexpr int LX_BOX = LX_TILE * 128;  // 128 rows x 32 fp32
 constexpr int LX_SMEM_LIMIT = 227 * 1024;
+constexpr int LX_STG_PITCH = 36;                          // floats per staged row (16-byte aligned, conflict-free)
+constexpr int LX_STG_BYTES = 32 * LX_STG_PITCH * 4;       // per epilogue warp
 
 enum { LX_PROJ = 0, LX_SILU = 1, LX_GI = 2 };
 
@@ -59,11 +65,13 @@ struct LxParams {
   int d;              // PROJ: group length
   float eps;
   int32_t* overflow;  // GI: set when a value does not fit fp16
+  int raw_stages, split_stages;
+  int staged;         // PROJ / SILU: rows go through a warp-private shared-memory transpose so that global stores are coalesced
   uint32_t idesc;
 };
 
 struct LxBars {
-  uint64_t raw_full[LX_RAW_STAGES], raw_empty[LX_RAW_STAGES], split_full[LX_SPLIT_STAGES], split_empty[LX_SPLIT_STAGES];
+  uint64_t raw_full[LX_MAX_RAW], raw_empty[LX_MAX_RAW], split_full[LX_MAX_SPLIT], split_empty[LX_MAX_SPLIT];
   uint64_t w_full, acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
@@ -102,16 +110,17 @@ linear_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   unsigned char* sWhi = smem;
   unsigned char* sWlo = sWhi + (size_t)P.ks * wbox;
   unsigned char* sRaw = sWlo + (size_t)P.ks * wbox;
-  unsigned char* sSplit = sRaw + LX_RAW_STAGES * LX_BOX;  // stage s: hi box at 2 s, lo box at 2 s + 1
-  LxBars* bars = reinterpret_cast<LxBars*>(sSplit + LX_SPLIT_STAGES * 2 * LX_BOX);
+  unsigned char* sSplit = sRaw + (size_t)P.raw_stages * LX_BOX;  // stage s: hi box at 2 s, lo box at 2 s + 1
+  unsigned char* sStage = sSplit + (size_t)P.split_stages * 2 * LX_BOX;
+  LxBars* bars = reinterpret_cast<LxBars*>(sStage + (P.staged ? LX_EPI_WARPS * LX_STG_BYTES : 0));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < LX_RAW_STAGES; ++s) {
+    for (int s = 0; s < LX_MAX_RAW; ++s) {
       mbar_init(&bars->raw_full[s], 1);
       mbar_init(&bars->raw_empty[s], 32 * LX_SPLIT_WARPS);
     }
-    for (int s = 0; s < LX_SPLIT_STAGES; ++s) {
+    for (int s = 0; s < LX_MAX_SPLIT; ++s) {
       mbar_init(&bars->split_full[s], 32 * LX_SPLIT_WARPS);
       mbar_init(&bars->split_empty[s], 1);
     }
@@ -134,6 +143,8 @@ linear_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
+  // (each role changes its register budget inside its own branch, so that ptxas allocates that branch against it)
+  if (warp < LX_EPI_WARP0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LX_CTL_REGS));
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
@@ -145,8 +156,8 @@ linear_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int ib = 0;
       for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
         for (int ks = 0; ks < P.ks; ++ks, ++ib) {
-          const int s = ib % LX_RAW_STAGES;
-          mbar_wait(&bars->raw_empty[s], ((uint32_t)(ib / LX_RAW_STAGES) & 1u) ^ 1u);
+          const int s = ib % P.raw_stages;
+          mbar_wait(&bars->raw_empty[s], ((uint32_t)(ib / P.raw_stages) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&bars->raw_full[s], LX_BOX);
           tma_load_2d(sRaw + (size_t)s * LX_BOX, &tmA, &bars->raw_full[s], ks * 32, tile * LX_TILE);
         }
@@ -164,8 +175,8 @@ linear_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t d_tmem = tmem + (uint32_t)acc * 256u;
       for (int ks = 0; ks < P.ks; ++ks, ++ib) {
-        const int s = ib % LX_SPLIT_STAGES;
-        mbar_wait(&bars->split_full[s], (uint32_t)(ib / LX_SPLIT_STAGES) & 1u);
+        const int s = ib % P.split_stages;
+        mbar_wait(&bars->split_full[s], (uint32_t)(ib / P.split_stages) & 1u);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t a_hi = sSa + (uint32_t)(2 * s) * LX_BOX, a_lo = a_hi + LX_BOX;
@@ -185,21 +196,23 @@ linear_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
       }
     }
-  } else if (warp < LX_EPI_WARP0) {
+  } else if (warp < 2 + LX_SPLIT_WARPS) {
     // =============================== splitter (warps 2..5) ===============================
     const int t = tid - 64;  // 0..127
     int ib = 0;
     for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
       for (int ks = 0; ks < P.ks; ++ks, ++ib) {
-        const int s = ib % LX_RAW_STAGES, s2 = ib % LX_SPLIT_STAGES;
-        mbar_wait(&bars->raw_full[s], (uint32_t)(ib / LX_RAW_STAGES) & 1u);
-        mbar_wait(&bars->split_empty[s2], ((uint32_t)(ib / LX_SPLIT_STAGES) & 1u) ^ 1u);
+        const int s = ib % P.raw_stages, s2 = ib % P.split_stages;
+        mbar_wait(&bars->raw_full[s], (uint32_t)(ib / P.raw_stages) & 1u);
+        mbar_wait(&bars->split_empty[s2], ((uint32_t)(ib / P.split_stages) & 1u) ^ 1u);
         const uint4* src = reinterpret_cast<const uint4*>(sRaw + (size_t)s * LX_BOX);
         uint4* dhi = reinterpret_cast<uint4*>(sSplit + (size_t)(2 * s2) * LX_BOX);
         uint4* dlo = reinterpret_cast<uint4*>(sSplit + (size_t)(2 * s2 + 1) * LX_BOX);
 #pragma unroll
-        for (int i = 0; i < LX_BOX / 16 / 128; ++i) {
-          const uint4 v = src[i * 128 + t];
+        constexpr int NT = 32 * LX_SPLIT_WARPS;
+#pragma unroll 4
+        for (int i = 0; i < LX_BOX / 16 / NT; ++i) {
+          const uint4 v = src[i * NT + t];
           uint4 h, l;
           h.x = v.x & 0xFFFFE000u;
           h.y = v.y & 0xFFFFE000u;
@@ -209,16 +222,17 @@ linear_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
           l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
           l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-          dhi[i * 128 + t] = h;
-          dlo[i * 128 + t] = l;
+          dhi[i * NT + t] = h;
+          dlo[i * NT + t] = l;
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tcgen05 operand reads
         mbar_arrive(&bars->split_full[s2]);
         mbar_arrive(&bars->raw_empty[s]);
       }
     }
-  } else {
-    // =============================== epilogue (warps 6..13) ===============================
+  } else if (warp >= LX_EPI_WARP0) {
+    // =============================== epilogue (warps 8..15) ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(LX_EPI_REGS));
     const int quarter = warp & 3;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int nch = P.nc / 32;
@@ -234,6 +248,42 @@ linear_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int64_t row = (int64_t)tile * LX_TILE + quarter * 32 + lane;
       const bool live = row < P.M;
       uint32_t v[32];
+      // rows of this warp's 32-row group that exist (fp32 outputs) / that exist in the padded fp16 outputs
+      const int64_t row0 = (int64_t)tile * LX_TILE + quarter * 32;
+      const int live_rows = (int)(P.M - row0 < 0 ? 0 : (P.M - row0 > 32 ? 32 : P.M - row0));
+      const int pad_rows = (int)(P.M_pad - row0 < 0 ? 0 : (P.M_pad - row0 > 32 ? 32 : P.M_pad - row0));
+      float* stg = reinterpret_cast<float*>(sStage + (size_t)(warp - LX_EPI_WARP0) * LX_STG_BYTES);
+      // 32 x 32 fp32 chunk (lane = row) -> global rows, 128-byte segments per row, through the warp's staging buffer:
+      // stg_put4 writes four consecutive values of this lane's row, flush_f32 sends the staged chunk out
+      auto stg_put4 = [&](int j4, float a0, float a1, float a2, float a3) __attribute__((always_inline)) {
+        *reinterpret_cast<float4*>(stg + lane * LX_STG_PITCH + 4 * j4) = make_float4(a0, a1, a2, a3);
+      };
+      auto flush_f32 = [&](float* g, int64_t pitch) __attribute__((always_inline)) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = (lane >> 3) + 4 * i, c4 = lane & 7;
+          const float4 t = *reinterpret_cast<const float4*>(stg + r * LX_STG_PITCH + 4 * c4);
+          if (r < live_rows)
+            st_global_v4(g + (int64_t)r * pitch + 4 * c4, __float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z),
+                         __float_as_uint(t.w));
+        }
+        __syncwarp();
+      };
+      // the same chunk as packed fp16 pairs (h[i] = columns 2i, 2i + 1): 64-byte segments per row (staged rows of 80 bytes)
+      auto put_f16 = [&](const uint32_t (&h)[16], uint16_t* g, int64_t pitch) __attribute__((always_inline)) {
+        uint4* s4 = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s4[lane * 5 + j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (lane >> 2) + 8 * i, pc = lane & 3;
+          const uint4 t = s4[r * 5 + pc];
+          if (r < pad_rows) st_global_v4(g + (int64_t)r * pitch + 8 * pc, t.x, t.y, t.z, t.w);
+        }
+        __syncwarp();
+      };
       if (P.mode == LX_PROJ) {
         const int cpg = P.d / 32;  // chunks per group
         for (int g0 = c_lo; g0 < c_hi; g0 += cpg) {
@@ -241,11 +291,16 @@ linear_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int c = g0; c < g0 + cpg; ++c) {
             tmem_ld_x32(taddr + (uint32_t)c * 32u, v);
             tmem_ld_wait_bind32(v);
-            const float* b = P.bias + P.n0 + c * 32;
+            const float4* b4 = reinterpret_cast<const float4*>(P.bias + P.n0 + c * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x = __uint_as_float(v[j]) + __ldg(b + j);
-              ss = fmaf(x, x, ss);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 t = __ldg(b4 + j4);
+              const float x0 = __uint_as_float(v[4 * j4]) + t.x, x1 = __uint_as_float(v[4 * j4 + 1]) + t.y;
+              const float x2 = __uint_as_float(v[4 * j4 + 2]) + t.z, x3 = __uint_as_float(v[4 * j4 + 3]) + t.w;
+              ss = fmaf(x0, x0, ss);
+              ss = fmaf(x1, x1, ss);
+              ss = fmaf(x2, x2, ss);
+              ss = fmaf(x3, x3, ss);
             }
           }
           const float nrm = fmaxf(sqrtf(ss), P.eps);
@@ -253,71 +308,76 @@ linear_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int c = g0; c < g0 + cpg; ++c) {
             tmem_ld_x32(taddr + (uint32_t)c * 32u, v);
             tmem_ld_wait_bind32(v);
-            const float* b = P.bias + P.n0 + c * 32;
-            float y[32];
+            const float4* b4 = reinterpret_cast<const float4*>(P.bias + P.n0 + c * 32);
+            uint32_t h[16];
+            // x / nrm, correctly rounded: quotient estimate + one Newton step on it
+            auto quot = [&](float x) __attribute__((always_inline)) {
+              const float q = x * r;
+              return live ? fmaf(fmaf(-q, nrm, x), r, q) : 0.f;
+            };
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x = __uint_as_float(v[j]) + __ldg(b + j);
-              float q = x * r;
-              q = fmaf(fmaf(-q, nrm, x), r, q);  // x / nrm, correctly rounded (one Newton step on the quotient)
-              y[j] = live ? q : 0.f;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 t = __ldg(b4 + j4);
+              const float q0 = quot(__uint_as_float(v[4 * j4]) + t.x), q1 = quot(__uint_as_float(v[4 * j4 + 1]) + t.y);
+              const float q2 = quot(__uint_as_float(v[4 * j4 + 2]) + t.z), q3 = quot(__uint_as_float(v[4 * j4 + 3]) + t.w);
+              stg_put4(j4, q0, q1, q2, q3);
+              h[2 * j4] = pack_half2(q0, q1);
+              h[2 * j4 + 1] = pack_half2(q2, q3);
             }
-            if (live) {
-              float* o = P.out_f32 + row * P.pitch_f32 + P.n0 + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                st_global_v4(o + j, __float_as_uint(y[j]), __float_as_uint(y[j + 1]), __float_as_uint(y[j + 2]),
-                             __float_as_uint(y[j + 3]));
-            }
-            if (P.out_half != nullptr && row < P.M_pad) {
-              uint16_t* o = P.out_half + row * P.pitch_half + P.n0 + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                st_global_v4(o + j, pack_half2(y[j], y[j + 1]), pack_half2(y[j + 2], y[j + 3]),
-                             pack_half2(y[j + 4], y[j + 5]), pack_half2(y[j + 6], y[j + 7]));
-            }
+            const int col = P.n0 + c * 32;
+            flush_f32(P.out_f32 + row0 * P.pitch_f32 + col, P.pitch_f32);
+            if (P.out_half != nullptr) put_f16(h, P.out_half + row0 * P.pitch_half + col, P.pitch_half);
           }
         }
       } else {
-        for (int c = c_lo; c < c_hi; ++c) {
-          tmem_ld_x32(taddr + (uint32_t)c * 32u, v);
-          tmem_ld_wait_bind32(v);
+        uint32_t v2[32];
+        auto chunk = [&](const uint32_t (&u)[32], int c) __attribute__((always_inline)) {
           const int col = P.n0 + c * 32;  // first column of the chunk within the whole layer
           if (P.mode == LX_SILU) {
-            if (live) {
-              const float* b = P.bias + col;
-              float* o = P.out_f32 + row * P.pitch_f32 + col;
-              float y[32];
+            // x / (1 + exp(-x)) from ex2.approx / rcp.approx (~2^-21 relative, below the fp32 rounding noise of the layer
+            // that follows; expf + the IEEE division cost ~28 dependent instructions per element and made this
+            // epilogue the bottleneck of the build: 394 us of 1.19 ms)
+            const float4* b4 = reinterpret_cast<const float4*>(P.bias + col);
+            auto silu = [&](float x) __attribute__((always_inline)) { return __fdividef(x, 1.f + __expf(-x)); };
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float x = __uint_as_float(v[j]) + __ldg(b + j);
-                y[j] = x / (1.f + expf(-x));
-              }
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                st_global_v4(o + j, __float_as_uint(y[j]), __float_as_uint(y[j + 1]), __float_as_uint(y[j + 2]),
-                             __float_as_uint(y[j + 3]));
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 t = __ldg(b4 + j4);
+              stg_put4(j4, silu(__uint_as_float(u[4 * j4]) + t.x), silu(__uint_as_float(u[4 * j4 + 1]) + t.y),
+                       silu(__uint_as_float(u[4 * j4 + 2]) + t.z), silu(__uint_as_float(u[4 * j4 + 3]) + t.w));
             }
-          } else if (col < P.n_f32) {  // GI, fp32 part
+            flush_f32(P.out_f32 + row0 * P.pitch_f32 + col, P.pitch_f32);
+          } else if (col < P.n_f32) {  // GI, fp32 part (direct stores: this launch has no staging buffer)
             if (live) {
               float* o = P.out_f32 + row * P.pitch_f32 + col;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) st_global_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 32; j += 4) st_global_v4(o + j, u[j], u[j + 1], u[j + 2], u[j + 3]);
             }
           } else if (row < P.M_pad) {  // GI, fp16 image (rows of W permuted into the coarse kernel's logit order)
             uint16_t* o = P.out_half + row * P.pitch_half + (col - P.n_f32);
             bool bad = false;
-            float y[32];
+            auto val = [&](int j) __attribute__((always_inline)) {
+              const float y = live ? __uint_as_float(u[j]) : 0.f;
+              bad |= !(fabsf(y) <= 65504.f);
+              return y;
+            };
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              y[j] = live ? __uint_as_float(v[j]) : 0.f;
-              bad |= !(fabsf(y[j]) <= 65504.f);
+            for (int j = 0; j < 32; j += 8) {
+              const uint32_t p0 = pack_half2(val(j), val(j + 1)), p1 = pack_half2(val(j + 2), val(j + 3));
+              const uint32_t p2 = pack_half2(val(j + 4), val(j + 5)), p3 = pack_half2(val(j + 6), val(j + 7));
+              st_global_v4(o + j, p0, p1, p2, p3);
             }
             if (bad) atomicOr(P.overflow, 1);
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              st_global_v4(o + j, pack_half2(y[j], y[j + 1]), pack_half2(y[j + 2], y[j + 3]), pack_half2(y[j + 4], y[j + 5]),
-                           pack_half2(y[j + 6], y[j + 7]));
+          }
+        };
+        if (c_lo < c_hi) tmem_ld_x32(taddr + (uint32_t)c_lo * 32u, v);
+        for (int c = c_lo; c < c_hi; c += 2) {  // the next chunk's TMEM load is in flight while this one is converted
+          tmem_ld_wait_bind32(v);
+          if (c + 1 < c_hi) tmem_ld_x32(taddr + (uint32_t)(c + 1) * 32u, v2);
+          chunk(v, c);
+          if (c + 1 < c_hi) {
+            tmem_ld_wait_bind32(v2);
+            if (c + 2 < c_hi) tmem_ld_x32(taddr + (uint32_t)(c + 2) * 32u, v);
+            chunk(v2, c + 1);
           }
         }
       }
@@ -371,11 +431,15 @@ int lx_encode(CUtensorMap* m, const float* base, uint64_t cols, uint64_t rows, u
   return MOL_OK;
 }
 
-// largest column chunk whose hi + lo weights fit next to the pipeline stages
-int lx_chunk_cols(int K) {
-  const size_t avail = LX_SMEM_LIMIT - 2048 - (size_t)LX_RAW_STAGES * LX_BOX - (size_t)LX_SPLIT_STAGES * 2 * LX_BOX;
+// Shared-memory plan of a launch: weights (hi + lo) of the column chunk | raw stages | split stages | staging | barriers.
+// Staged modes (PROJ / SILU) keep the chunk <= 128 columns so that the transposing store buffers and a deeper TMA ring fit.
+constexpr size_t LX_FIXED = 2048;  // alignment slack + barriers
+int lx_chunk_cols(int K, bool staged) {
+  const size_t stage_bytes = staged ? (size_t)LX_EPI_WARPS * LX_STG_BYTES : 0;
+  const size_t avail = LX_SMEM_LIMIT - LX_FIXED - stage_bytes - 2 * (size_t)LX_BOX - 2 * (size_t)LX_BOX;  // >= 2 raw + 1 split
   int nc = (int)(avail / ((size_t)K * 4 * 2));
-  if (nc > 256) nc = 256;
+  const int cap = staged ? 128 : 256;
+  if (nc > cap) nc = cap;
   return nc / 64 * 64;
 }
 
@@ -390,7 +454,8 @@ int lx_layer(const float* A, int64_t M, int K, const float* W_hi, const float* W
     MOL_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     sms = n;
   }
-  const int chunk = lx_chunk_cols(K);
+  P.staged = (P.mode == LX_PROJ || P.mode == LX_SILU) ? 1 : 0;
+  const int chunk = lx_chunk_cols(K, P.staged != 0);
   MOL_CHECK_ARG(chunk >= 64, "linear_x3: K=%d too large", K);
   const int64_t rows = P.M_pad > M ? P.M_pad : M;
   P.M = M;
@@ -405,9 +470,15 @@ int lx_layer(const float* A, int64_t M, int K, const float* W_hi, const float* W
     P.idesc = lx_idesc_tf32(LX_TILE, nc);
     MOL_TRY(lx_encode(&tmWhi, W_hi, (uint64_t)K, (uint64_t)n_rows_w, (uint32_t)nc));
     MOL_TRY(lx_encode(&tmWlo, W_lo, (uint64_t)K, (uint64_t)n_rows_w, (uint32_t)nc));
-    const size_t smem = 1024 + 2 * (size_t)P.ks * nc * 128 + (size_t)LX_RAW_STAGES * LX_BOX +
-                        (size_t)LX_SPLIT_STAGES * 2 * LX_BOX + sizeof(LxBars) + 64;
-    MOL_CHECK_ARG(smem <= (size_t)LX_SMEM_LIMIT, "linear_x3: shared memory %zu", smem);
+    // what is left after the weights goes to the pipeline: a second split stage when there is room for >= 2 raw stages
+    // besides it, the rest to the TMA ring (bytes in flight are what the HBM-bound layers need)
+    const size_t used = LX_FIXED + 2 * (size_t)P.ks * nc * 128 + (P.staged ? (size_t)LX_EPI_WARPS * LX_STG_BYTES : 0);
+    const int boxes = (int)(((size_t)LX_SMEM_LIMIT - used) / LX_BOX);
+    MOL_CHECK_ARG(boxes >= 4, "linear_x3: shared memory (K=%d, %d columns)", K, nc);
+    P.split_stages = boxes >= 6 ? 2 : 1;
+    int raw = boxes - 2 * P.split_stages;
+    P.raw_stages = raw > LX_MAX_RAW ? LX_MAX_RAW : raw;
+    const size_t smem = used + (size_t)(P.raw_stages + 2 * P.split_stages) * LX_BOX;
     const int grid = P.tiles < sms ? P.tiles : sms;
     linear_x3_kernel<<<grid, LX_THREADS, smem, st>>>(tmA, tmWhi, tmWlo, P);
     MOL_LAUNCH_CHECK();
@@ -424,7 +495,7 @@ bool index_build_x3_supported(const mol_shape_t& s, const mol_index_t& ix) {
   if (!(D.Dx % 32 == 0 && D.Dx <= 128 && D.Hgi % 32 == 0 && D.Hgi <= 128 && D.L % 32 == 0)) return false;
   if (!(D.d == 32 || D.d == 64 || D.d == 128)) return false;
   // every launch of the projection (a column chunk, or the remainder) must give each epilogue half whole l2-norm groups
-  const int chunk = lx_chunk_cols(D.Dx);
+  const int chunk = lx_chunk_cols(D.Dx, true);
   if (chunk < 2 * D.d || chunk % (2 * D.d) != 0 || (D.Px * D.d) % (2 * D.d) != 0) return false;
   return ix.num_items >= 1024 && reinterpret_cast<uintptr_t>(ix.raw_items) % 16 == 0;
 }
