@@ -482,7 +482,7 @@ def test_mol_avg_top_k_recall_vs_brute_force_large():
 @pytest.mark.parametrize("name", ["next_naive_8x8x32", "next_naive_8x4x64_uid", "next_comb_8x8x32", "next_comb_8x4x64_uid"])
 def test_mol_naive_comb_top_k_matches_reference(name):
     from rails_b200.indexing.mol_top_k import MoLCombTopK, MoLNaiveTopK
-    from tests.test_next_oracle_golden import assert_union_equal, load_avg
+    from tests.test_next_oracle_golden import assert_union_equal_tie_aware, load_avg
 
     g = load_avg(name)
     mol, _ = build_module(g["cfg"], g["sd"], DEV)
@@ -493,7 +493,8 @@ def test_mol_naive_comb_top_k_matches_reference(name):
         top = MoLNaiveTopK(mol, items, ids, g["k_per_group"])
     kw = {} if g["user_ids"] is None else {"user_ids": g["user_ids"].to(DEV)}
     s, i = top(g["queries"].to(DEV), k=10, **kw)
-    assert_union_equal(s.cpu(), i.cpu(), g["ref_scores_f32"], g["ref_ids_f32"], SCORE_TOL)
+    # (candidates 1.3e-6 apart in the reference swap places between the tensor-core and the CUDA-core index build)
+    assert_union_equal_tie_aware(s.cpu(), i.cpu(), g["ref_scores_f32"], g["ref_ids_f32"], SCORE_TOL)
 
 
 def test_mol_naive_comb_top_k_large_vs_oracle():
