@@ -329,6 +329,70 @@ def secondary_block(dev, mode, north=None):
                                                "hbm_gbs_algorithmic": index.N * 640 / (gms * 1e-3) / 1e9}
                 del g
         out["batch_sweep_1m_top100"] = sweep
+        if len(north) > 5:
+            out["next_rows_1m"] = next_rows_block(dev, north[5], index, q_dev, k)
+    return out
+
+
+def next_rows_block(dev, mol, index, q_dev, k):
+    """SURVEY.md §8 rows f1-f4 on the north-star corpus (1M items, 8x8x32): index build, seen-item exclusion inside the
+    search vs the over-fetch + mask recipe, the approximate MoL modules and MIPS - the streaming tensor-core paths and
+    (for reference) the materialised-matrix paths they replace (MOL_B200_DOTFILTER=0 / MOL_B200_INDEX_X3=0)."""
+    from rails_b200 import engine
+    from rails_b200.indexing.candidate_index import CandidateIndex
+    from rails_b200.indexing.mips_top_k import MIPSBruteForceTopK
+    from rails_b200.indexing.mol_top_k import MoLAvgTopK, MoLBruteForceTopK, MoLCombTopK, MoLNaiveTopK
+
+    items, ids = index.raw, index.ids
+    it3, id2 = items.unsqueeze(0), ids.unsqueeze(0)
+    out = {}
+
+    def timed(fn, steps=5, warmup=2):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    w = mol.packed_weights(dev)
+    saved = {v: os.environ.get(v) for v in ("MOL_B200_DOTFILTER", "MOL_B200_INDEX_X3")}
+    try:
+        for tag, env in (("tensor", "1"), ("cuda_core", "0")):
+            os.environ["MOL_B200_INDEX_X3"] = env
+            out[f"f1_index_build_ms_{tag}"] = timed(lambda: engine.IndexHandle(w, items, ids), 3, 1)
+        os.environ["MOL_B200_INDEX_X3"] = "1"
+        top = MoLBruteForceTopK(mol, it3, id2)
+        ci = CandidateIndex(ids=id2, embeddings=it3)
+        B = q_dev.size(0)
+        inv = torch.randint(1, index.N + 1, (B, 211), device=dev)
+        out["f2_seen_items_B512_n0_211_ms_in_search"] = timed(lambda: ci.get_top_k_outputs(q_dev, k, {}, top, inv), 3, 1)
+        out["f2_seen_items_B512_n0_211_ms_overfetch_mask"] = timed(
+            lambda: ci.get_top_k_outputs(q_dev, k, {}, top, inv, truncate_k_prime_to=k + 211), 3, 1)
+        out["f2_no_seen_items_B512_ms"] = timed(lambda: top(q_dev, k=k), 3, 1)
+        for tag, env in (("streaming", "1"), ("matrix", "0")):
+            os.environ["MOL_B200_DOTFILTER"] = env
+            mips = MIPSBruteForceTopK(it3, id2)
+            for b in ((1, 64, 512) if env == "1" else (512,)):
+                out[f"f4_mips_top{k}_B{b}_ms_{tag}"] = timed(lambda: mips(q_dev[:b], k=k), 10, 3)
+            if env == "1":
+                out["f4_mips_stats"] = mips.last_search_stats()
+            for name, mod in (("avg2000", MoLAvgTopK(mol, it3, id2, 2000)), ("naive_kpg5", MoLNaiveTopK(mol, it3, id2, 5)),
+                              ("comb_kpg5_avg200", MoLCombTopK(mol, it3, id2, 200, 5))):
+                out[f"f3_mol_{name}_B64_ms_{tag}"] = timed(lambda: mod(q_dev[:64], k=k), 3, 1)
+                if env == "1":
+                    out[f"f3_mol_{name}_stats"] = mod.last_search_stats()
+            del mips
+    finally:
+        for v, val in saved.items():
+            if val is None:
+                os.environ.pop(v, None)
+            else:
+                os.environ[v] = val
     return out
 
 
@@ -567,7 +631,7 @@ def main():
 
     secondary = None
     if rank == 0 and world == 1 and args.config == "north" and not args.no_secondary and args.items is None and args.batch is None:
-        secondary = secondary_block(dev, mode, (weights, index, wsp, q_dev, k))
+        secondary = secondary_block(dev, mode, (weights, index, wsp, q_dev, k, mol))
 
     if rank == 0:
         par = {"single": "single GPU", "replicate": f"corpus replicated, queries split x{world}, one all-gather",
