@@ -7,7 +7,7 @@ from rails_b200.indexing.mol_top_k import MoLBruteForceTopK
 from tests.helpers import CFG_8x8x32, build_module, synthetic_inputs
 dev = torch.device("cuda:0")
 mol, _ = build_module(CFG_8x8x32, None, dev, seed=0)
-items, ids, q, _ = synthetic_inputs(CFG_8x8x32, 1_000_000, 8, 0, dev)
+items, ids, q, _ = synthetic_inputs(CFG_8x8x32, 1_000_000, 64, 0, dev)
 top = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0))
 b = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 top(q[:b], k=100)
