@@ -351,6 +351,41 @@ row_norm_max_kernel(const float* __restrict__ items, int64_t N, int64_t pitch, i
   if (lane == 0 && best > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(best) * 1.000001f));
 }
 
+// Filter level of a row from its S sampled values, one CTA per row: every thread keeps the maximum of its strided slice
+// (S / 256 values), the 256 maxima are sorted and the m-th largest is the level.  When two of the row's m largest values
+// share a slice the result is the (m+1)-th largest instead - the level is a heuristic (it only steers how many items
+// survive; completeness is proven afterwards, mol_dotfilter.cuh), and this is 67 MB read once instead of a (rows, S) radix
+// select (82 us for 512 rows).
+constexpr int SL_THREADS = 256;
+__global__ void __launch_bounds__(SL_THREADS)
+sample_level_kernel(const float* __restrict__ samp, int64_t S, int m, float* __restrict__ level_out) {
+  __shared__ float sv[SL_THREADS];
+  const int r = blockIdx.x, t = threadIdx.x;
+  const float4* row = reinterpret_cast<const float4*>(samp + (int64_t)r * S);  // S % 128 == 0, rows 16-byte aligned
+  float best = -CUDART_INF_F;
+  for (int64_t i = t; i < S / 4; i += SL_THREADS) {
+    const float4 v = __ldg(row + i);
+    best = fmaxf(best, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  sv[t] = best;
+  __syncthreads();
+  for (int size = 2; size <= SL_THREADS; size <<= 1) {  // bitonic sort, descending
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int p = t ^ stride;
+      if (p > t) {
+        const bool desc = (t & size) == 0;
+        const float a = sv[t], b = sv[p];
+        if ((a < b) == desc) {
+          sv[t] = b;
+          sv[p] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (t == 0) level_out[r] = sv[m - 1 < SL_THREADS ? m - 1 : SL_THREADS - 1];
+}
+
 __global__ void norm_publish_kernel(float* cache) {
   if (cache[0] < 0.f) cache[0] = cache[1];
 }
@@ -366,7 +401,7 @@ __global__ void level_kernel(const float* __restrict__ samp_top, int m, const fl
   float ss = 0.f;
   for (int k = 0; k < K; ++k) ss = fmaf(q[k], q[k], ss);
   const float e = (1.0f / 256.0f) * sqrtf(ss) * (xmax ? xmax[0] : xmax_host) * 1.0001f;
-  const float t = samp_top[(int64_t)r * m + (m - 1)];
+  const float t = samp_top[(int64_t)r * m + (m - 1)];  // (m = 1: one level per row, from sample_level_kernel)
   level[r] = t;
   check[r] = t + e;
 }
@@ -648,7 +683,11 @@ int dot_topk_run(const DotTopkPlan& p, const float* items, int64_t pitch, int co
       MOL_TRY(launch_dot_filter(items, N, pitch, col0, K, Qc + (int64_t)c0 * q_pitch, q_pitch, n, nst, p.tile_stride,
                                 p.samp + (int64_t)c0 * p.S, p.S, nullptr, nullptr, nullptr, nullptr, 0, 0, st));
     }
-    {
+    const bool bucket_level = m <= 64 && p.S >= 4 * SL_THREADS * 8;  // small m: maxima of 256 slices per row are enough
+    if (bucket_level) {
+      sample_level_kernel<<<rc, SL_THREADS, 0, st>>>(p.samp, p.S, m, p.samp_top);
+      MOL_LAUNCH_CHECK();
+    } else {
       // (segments of ~4k values: the one-CTA-per-row select of 32k values took 68 us for 512 rows)
       int S1 = (int)(p.S / 4096);
       S1 = S1 < 1 ? 1 : (S1 > 8 ? 8 : S1);
@@ -664,7 +703,8 @@ int dot_topk_run(const DotTopkPlan& p, const float* items, int64_t pitch, int co
       }
       MOL_TRY(launch_select_final_i32(sel, pay, sn, sn, rc, m, p.samp_top, nullptr, nullptr, nullptr, nullptr, st));
     }
-    level_kernel<<<(rc + 127) / 128, 128, 0, st>>>(p.samp_top, m, Qc, q_pitch, K, xmax_dev, xmax_host, p.level, p.check, rc);
+    level_kernel<<<(rc + 127) / 128, 128, 0, st>>>(p.samp_top, bucket_level ? 1 : m, Qc, q_pitch, K, xmax_dev, xmax_host, p.level,
+                                                   p.check, rc);
     MOL_LAUNCH_CHECK();
     MOL_CUDA(cudaMemsetAsync(p.cnt, 0, (size_t)rc * sizeof(int32_t), st));
     MOL_CUDA(cudaMemsetAsync(p.cidx, 0xFF, (size_t)rc * cap * sizeof(int32_t), st));
