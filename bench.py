@@ -523,6 +523,7 @@ def main():
     ms_step = ms_total / args.steps
     value = B / (ms_step * 1e-3)
     stats = engine.search_stats(wsp) if world == 1 else top.last_search_stats()  # counters of the last timed search on this rank
+    tensor_path = bool(stats.get("tensor_path", tensor_path))  # (MODE_AUTO serves tiny searches with the fp32 kernel)
 
     # ---- the scoring kernel alone: a separate pass with the library's CUDA-event profiling switched on
     prof_steps = min(args.steps, 3)

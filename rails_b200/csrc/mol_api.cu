@@ -211,8 +211,22 @@ static int coarse_candidates(int k, int64_t N) {
   return (int)kp;
 }
 
-static bool use_tensor(const mol_shape_t& s, int mode) {
+// MOL_MODE_AUTO below ~32k (query, item) pairs: the fp32 kernel over every pair (~15 us + one select) beats the tensor
+// path's fixed sequence - query records, coarse pass, select, rescoring, select, acceptance test, idle fallback launches
+// (~75 us; BASELINE config 1: one query over 3883 items, 116 -> 75 us of kernels).  MOL_B200_TENSOR_MIN_PAIRS overrides it
+// (the test suite sets 0 so that MODE_AUTO keeps exercising the tensor path on the small reference fixtures).
+constexpr int64_t kTensorMinPairs = 1ll << 15;
+static int64_t tensor_min_pairs() {
+  const char* e = getenv("MOL_B200_TENSOR_MIN_PAIRS");
+  if (e) {
+    const long long v = atoll(e);
+    if (v >= 0) return (int64_t)v;
+  }
+  return kTensorMinPairs;
+}
+static bool use_tensor(const mol_shape_t& s, int mode, int64_t B, int64_t N) {
   if (mode == MOL_MODE_EXACT) return false;
+  if (mode == MOL_MODE_AUTO && B * N < tensor_min_pairs()) return false;
   return coarse_supported(s);
 }
 
@@ -235,7 +249,7 @@ static int plan_search(const mol_shape_t& s, int64_t N, int B, int k, int mode, 
                        size_t cap, SearchWs* ws, int n0 = 0) {
   Dims D = dims_of(s);
   Arena a(base, cap);
-  const bool tensor = use_tensor(s, mode);
+  const bool tensor = use_tensor(s, mode, B, N);
   ws->stats = a.take<int32_t>(kNumStats);  // (offset 0 of the workspace: mol_search_stats reads it back)
   ws->pre = a.take<float>((size_t)B * 2 * D.Hq);
   ws->h = a.take<float>((size_t)B * D.Hq);
@@ -470,7 +484,7 @@ static int search_impl(const mol_shape_t& s, const mol_weights_t& w, const mol_i
                        const int64_t* invalid_ids = nullptr) {
   Dims D = dims_of(s);
   const int64_t N = ix.num_items;
-  const bool tensor = use_tensor(s, mode);
+  const bool tensor = use_tensor(s, mode, B, N);
   SearchWs ws = ws_in;
   Prepared prep;
   {

@@ -284,3 +284,26 @@ def test_cuda_graph_search_equals_eager():
         s, i = top1(g["queries"].to(DEV), k=g["k"], user_ids=u)
         r = O.compare_top_k(s, i, g["ref_scores"], g["item_ids"], g["k"], SCORE_TOL, TIE_TOL)
         assert r["ok"] == 1.0, r
+
+
+def test_small_searches_take_the_exact_kernel_in_auto_mode(monkeypatch):
+    """Below 2^15 (query, item) pairs MODE_AUTO runs the fp32 kernel over every pair (BASELINE config 1: one query over
+    3883 items) - same answer as the tensor path and as MODE_EXACT, `tensor_path` = 0 in the stats."""
+    from tests.golden_util import load_golden
+
+    g = load_golden("cfg1_ml1m_ckpt")
+    mol, _ = build_module(g["cfg"], g["sd"], DEV)
+    items, ids = g["items"].to(DEV).unsqueeze(0), g["item_ids"].to(DEV).unsqueeze(0)
+    q, uid = g["queries"][:1].to(DEV), g["user_ids"][:1].to(DEV)
+    out = {}
+    for name, pairs in (("switch", None), ("tensor", "0")):
+        if pairs is None:
+            monkeypatch.delenv("MOL_B200_TENSOR_MIN_PAIRS", raising=False)
+        else:
+            monkeypatch.setenv("MOL_B200_TENSOR_MIN_PAIRS", pairs)
+        s, i = MoLBruteForceTopK(mol, items, ids, mode=_lib.MODE_AUTO)(q, k=g["k"], user_ids=uid)
+        out[name] = (s, i, _stats(mol))
+    assert out["switch"][2]["tensor_path"] == 0 and out["tensor"][2]["tensor_path"] == 1
+    assert torch.equal(out["switch"][1], out["tensor"][1]) and torch.equal(out["switch"][0], out["tensor"][0])
+    r = O.compare_top_k(out["switch"][0][:1], out["switch"][1][:1], g["ref_scores"][:1], g["item_ids"], g["k"], 1e-3, 1e-4)
+    assert r["ok"] == 1.0, r
