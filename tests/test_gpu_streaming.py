@@ -211,3 +211,50 @@ def test_tensor_core_index_build_matches_cuda_core_build(cfg, N, monkeypatch):
     gi_ref = O._mlp_silu(items[sl].cpu(), sd[O.K_GI_W1], sd[O.K_GI_B1], sd[O.K_GI_W2])
     assert (a["xsub_f32"][sl].cpu() - xs_ref.reshape(3000, -1)).abs().max().item() < 5e-6
     assert (a["gi_f32"][sl].cpu() - gi_ref).abs().max().item() < 5e-6 * max(gscale, 1.0)
+
+
+def test_streaming_modules_vs_cpu_oracle_directly():
+    """The streaming prefilters against the CPU restatement of the reference (oracle/next_oracle.py: mol_top_k.py:133-551,
+    mips_top_k.py:74-81) at a corpus size that takes the streaming path (>= 64k items) - not only against the materialised
+    GPU path.  Candidate sets may differ by fp32 near-ties at a selection boundary; the best items are identical."""
+    import numpy as np
+
+    from oracle import next_oracle as NO
+    from rails_b200.indexing.mips_top_k import MIPSBruteForceTopK
+    from rails_b200.indexing.mol_top_k import MoLAvgTopK, MoLCombTopK, MoLNaiveTopK
+
+    cfg = CFG_8x8x32
+    N, B, kpg, a, k = 80_000, 6, 8, 600, 20
+    mol, _ = build_module(cfg, None, DEV, seed=52)
+    items, ids, q, _ = synthetic_inputs(cfg, N, B, 52, DEV)
+    sd = {k_: v.detach().cpu() for k_, v in mol.state_dict().items()}
+    it3, id2 = items.unsqueeze(0), ids.unsqueeze(0)
+    # MoLAvgTopK
+    top = MoLAvgTopK(mol, it3, id2, a)
+    s, i = top(q, k=k)
+    assert top.last_search_stats()["filter_strategy"] == 1
+    rs, ri, _ = NO.mol_avg_top_k(cfg, sd, q.cpu(), items.cpu(), ids.cpu(), k, a)
+    same = np.mean([len(set(x.tolist()) & set(y.tolist())) / k for x, y in zip(i.cpu(), ri)])
+    assert same >= 0.99, same
+    assert (s.cpu() - rs).abs().max().item() < 1e-3 or same < 1.0
+    # MoLNaiveTopK / MoLCombTopK
+    for top, ref in (
+        (MoLNaiveTopK(mol, it3, id2, kpg), NO.mol_naive_top_k(cfg, sd, q.cpu(), items.cpu(), ids.cpu(), kpg)),
+        (MoLCombTopK(mol, it3, id2, a, kpg), NO.mol_comb_top_k(cfg, sd, q.cpu(), items.cpu(), ids.cpu(), a, kpg)),
+    ):
+        s, i = top(q, k=10)
+        assert top.last_search_stats()["filter_strategy"] == 1
+        rs, ri = ref
+        for b in range(B):
+            nv, rnv = int((s[b] > -32767.0).sum()), int((rs[b] > -32767.0).sum())
+            assert abs(nv - rnv) <= 2
+            assert torch.equal(i[b, :50].cpu(), ri[b, :50])
+            assert (s[b, :50].cpu() - rs[b, :50]).abs().max().item() < 1e-3
+    # MIPS: fp64 referee on the CPU
+    mips = MIPSBruteForceTopK(it3, id2)
+    s, i = mips(q, k=k)
+    assert mips.last_search_stats()["filter_strategy"] == 1
+    ref = q.double().cpu() @ items.double().cpu().t()
+    rs = ref.topk(k, dim=1).values
+    got = torch.gather(ref, 1, i.cpu() - 1)
+    assert (got - rs).abs().max().item() < 2e-5 and (s.cpu().double() - got).abs().max().item() < 2e-5
