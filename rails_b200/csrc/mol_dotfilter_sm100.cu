@@ -32,7 +32,9 @@ constexpr int DF_MAX_STAGES = 6;
 constexpr int DF_BOX_BYTES = DF_TILE * 128;  // 128 rows x 32 fp32
 constexpr int DF_MAX_CC = 256;
 constexpr int DF_SMEM_LIMIT = 227 * 1024;
-constexpr int DF_STAGE_CAP = 2048;  // survivors staged in shared memory between two drains
+constexpr int DF_STAGE_CAP = 1024;  // survivors staged in shared memory between two drains
+constexpr int DF_HIT_PITCH = 36;    // floats per lane of the hit-extraction buffer (16-byte aligned rows, conflict-free float4 stores)
+constexpr int DF_HIT_BYTES = 32 * DF_HIT_PITCH * 4;  // per epilogue warp
 
 struct DfParams {
   // sample mode (out != nullptr): out[col * ld + tile * 128 + row in tile] = value
@@ -115,7 +117,8 @@ dot_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   float* sStageVal = sLevel + DF_MAX_CC;
   int32_t* sStageRow = reinterpret_cast<int32_t*>(sStageVal + DF_STAGE_CAP);
   int32_t* sStageCol = sStageRow + DF_STAGE_CAP;
-  DfBars* bars = reinterpret_cast<DfBars*>(sStageCol + DF_STAGE_CAP);
+  float* sHit = reinterpret_cast<float*>(sStageCol + DF_STAGE_CAP);  // DF_EPI_WARPS x 32 lanes x DF_HIT_PITCH
+  DfBars* bars = reinterpret_cast<DfBars*>(reinterpret_cast<unsigned char*>(sHit) + DF_EPI_WARPS * DF_HIT_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -261,26 +264,27 @@ dot_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
               }
             };
-            // one pass per hit of this lane (almost always one): the first column >= jmin that passes
-            int jmin = 0;
-            for (;;) {
-              int fj = 32;
-              float fv = 0.f;
+            // hit extraction: a bit mask of the passing columns, the chunk's values parked in this lane's own row of a
+            // shared-memory buffer (no other lane touches it: no synchronisation), then one staged entry per set bit.
+            // (Selecting a register by a run-time column index is not possible; a select chain per hit cost ~260
+            // instructions where this costs ~80.)
+            float* mine = sHit + ((warp - 2) * 32 + lane) * DF_HIT_PITCH;
+            uint32_t mask = 0;
 #pragma unroll
-              for (int j4 = 7; j4 >= 0; --j4) {
-                const float4 t = lds_f4(lv + 16u * j4);
-                const float tt[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                for (int u = 3; u >= 0; --u) {
-                  const float x = __uint_as_float(v[4 * j4 + u]);
-                  const bool h = (x >= tt[u]) && (4 * j4 + u >= jmin);
-                  fv = h ? x : fv;
-                  fj = h ? 4 * j4 + u : fj;
-                }
-              }
-              if (fj == 32) break;
-              stage(cbase + fj, fv);
-              jmin = fj + 1;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 t = lds_f4(lv + 16u * j4);
+              const float x0 = __uint_as_float(v[4 * j4]), x1 = __uint_as_float(v[4 * j4 + 1]);
+              const float x2 = __uint_as_float(v[4 * j4 + 2]), x3 = __uint_as_float(v[4 * j4 + 3]);
+              mask |= (x0 >= t.x) ? (1u << (4 * j4)) : 0u;
+              mask |= (x1 >= t.y) ? (2u << (4 * j4)) : 0u;
+              mask |= (x2 >= t.z) ? (4u << (4 * j4)) : 0u;
+              mask |= (x3 >= t.w) ? (8u << (4 * j4)) : 0u;
+              *reinterpret_cast<float4*>(mine + 4 * j4) = make_float4(x0, x1, x2, x3);
+            }
+            while (mask != 0) {
+              const int j = __ffs((int)mask) - 1;
+              mask &= mask - 1;
+              stage(cbase + j, mine[j]);
             }
           }
         }
@@ -538,7 +542,8 @@ int launch_dot_filter(const float* items, int64_t N, int64_t pitch, int col0, in
     P.drain_every = every < 1 ? 1 : (every > 64 ? 64 : every);
   }
   const size_t fixed =
-      1024 + (size_t)P.ks * P.cc * 128 + DF_MAX_CC * sizeof(float) + (size_t)DF_STAGE_CAP * 12 + sizeof(DfBars) + 64;
+      1024 + (size_t)P.ks * P.cc * 128 + DF_MAX_CC * sizeof(float) + (size_t)DF_STAGE_CAP * 12 +
+      (size_t)DF_EPI_WARPS * DF_HIT_BYTES + sizeof(DfBars) + 64;
   int stages = (int)((DF_SMEM_LIMIT - fixed) / DF_BOX_BYTES);
   if (stages > DF_MAX_STAGES) stages = DF_MAX_STAGES;
   MOL_CHECK_ARG(stages >= 2, "dot filter: K=%d with %d query rows does not fit shared memory", K, P.cc);
