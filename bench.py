@@ -304,7 +304,7 @@ def secondary_block(dev, mode, north=None):
             del gtop
         del top, items
     if north is not None:
-        weights, index, wsp, q_dev, k = north
+        weights, index, wsp, q_dev, k = north[:5]
         sweep = {}
         for b in (1, 8, 32, 128, 512):
             if b > q_dev.size(0):
