@@ -602,11 +602,14 @@ def _nccl_worker(rank, world, port, out):
         full = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0))
         rs, ri = full(q, k)
         ok = bool(torch.equal(i, ri)) and bool(torch.equal(s, rs))
+        detail = {"shard_ids": bool(torch.equal(i, ri)), "shard_scores": bool(torch.equal(s, rs))}
         # query-split layout over the replicated corpus (ragged: 15 queries over 2 ranks).  Slices of <= 8 queries take the
         # small-batch prologue kernels, whose sums may differ from the 16-query batch in the last bit: ids equal, scores
-        # to 1e-5
+        # to 1e-4 (a last-bit change of Q_sub is amplified by 1 / tau = 20; the bar is 1e-3)
         s2, i2 = ReplicatedMoLBruteForceTopK(full)(q[:15], k)
-        ok = ok and bool(torch.equal(i2, ri[:15])) and float((s2 - rs[:15]).abs().max()) < 1e-5
+        ok = ok and bool(torch.equal(i2, ri[:15])) and float((s2 - rs[:15]).abs().max()) < 1e-4
+        detail.update(rep_ids=bool(torch.equal(i2, ri[:15])), rep_err=float((s2 - rs[:15]).abs().max()),
+                      rep_mismatch=int((i2 != ri[:15]).sum()))
         # k beyond the corpus: RuntimeError on every rank, before any collective
         try:
             ShardedMoLBruteForceTopK(local, hi - lo)(q, N + 1)
@@ -614,6 +617,7 @@ def _nccl_worker(rank, world, port, out):
         except RuntimeError as e:
             ok = ok and "out of range" in str(e)
         out[rank] = ok
+        out[f"detail{rank}"] = detail
     finally:
         dist.destroy_process_group()
 
@@ -630,4 +634,4 @@ def test_sharded_topk_two_gpus_equals_unsharded():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_nccl_worker, args=(2, port, out), nprocs=2, join=True)
-    assert out[0] is True and out[1] is True
+    assert out[0] is True and out[1] is True, dict(out)
