@@ -43,7 +43,9 @@ def parse():
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--config", default="north", choices=["north", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    p.add_argument("--config", default="north", choices=["north", "sweep", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                   help="north: BASELINE.json's north-star workload (its `secondary` block carries configs 1-3, the B sweep of "
+                        "SURVEY 8(d) and the next rows); sweep: the same line with the baseline legs skipped; cfgN: that config")
     p.add_argument("--items", type=int, default=None)
     p.add_argument("--batch", type=int, default=None)
     p.add_argument("--k", type=int, default=None)
@@ -54,7 +56,12 @@ def parse():
     p.add_argument("--no-secondary", action="store_true", help="skip the secondary configs / batch sweep block")
     p.add_argument("--no-cuda-graph", action="store_true", help="N > 1: launch each rank's search eagerly instead of as a CUDA graph")
     p.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-this-GPU baseline leg")
-    return p.parse_args()
+    args = p.parse_args()
+    if args.config == "sweep":  # the north-star line without the CPU / eager-GPU baseline legs: its secondary block IS the sweep
+        args.config = "north"
+        args.no_cpu_baseline = True
+        args.no_gpu_eager = True
+    return args
 
 
 # ---------------------------------------------------------------------------------------------- workloads
