@@ -44,6 +44,8 @@ def _check_vs_torch(items, ids, q, k, s, i):
         (131_072, 128, 33, 200),    # K = 128
         (100_000, 256, 130, 50),    # K = 256: 128 query rows per launch
         (1_000_000, 64, 1, 1),      # one query, k = 1
+        (70_000, 96, 5, 7),         # K = 96: three boxes per tile, 24 lanes per row in the norm pass
+        (66_000, 32, 8300, 3),      # more than 8192 query rows: two row chunks of the whole pipeline
     ],
 )
 def test_mips_streaming_equals_materialised(N, D, B, k, monkeypatch):
