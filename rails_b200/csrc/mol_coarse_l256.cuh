@@ -24,7 +24,24 @@
 
 namespace l256 {
 
-using v3::Walk32;
+// Walks a CTA's flat range [f0, f1) of (tile, query) units tile by tile, in 32-bit arithmetic (one division in all).
+struct Walk32 {
+  int f1, bc, tile, qa, qb, qa_next;
+  __device__ Walk32(int f0, int f1_, int bc_) : f1(f1_), bc(bc_), qa(0), qb(0) {
+    tile = f0 / bc - 1;  // (the only division)
+    qa_next = f0 - (tile + 1) * bc;
+  }
+  __device__ bool next() {
+    ++tile;
+    qa = qa_next;
+    qa_next = 0;
+    const int rest = f1 - tile * bc;
+    if (rest <= qa) return false;
+    qb = rest < bc ? rest : bc;
+    return true;
+  }
+  __device__ int n_mine(int s) const { return (qb - qa + 1 - s) / 2; }
+};
 
 constexpr int kThreadsL = 640;
 constexpr int kIssuerWarp = 16, kTmaWarp = 17;

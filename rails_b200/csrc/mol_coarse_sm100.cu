@@ -49,9 +49,6 @@ constexpr int kCtlWarp0 = kEpiThreads / 32;    // control warpgroup: issuer slot
 constexpr int kThreads = kEpiThreads + 4 * 32;
 // setmaxnreg split of the 64K-register file (the kernel is compiled for 640 threads -> 96 registers at launch)
 // (setmaxnreg only redistributes the CTA's own launch allocation: 640 x 96 = 61440 registers)
-#ifndef MOL_COARSE_V3
-#define MOL_COARSE_V3 0
-#endif
 #ifndef MOL_HID_F16
 #define MOL_HID_F16 1  // measured (round 2): 33.2 -> 32.4 ms per 512 x 1M step, max coarse-vs-exact error 0.023 -> 0.026
 #endif
@@ -841,7 +838,6 @@ mol_coarse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 
-#include "mol_coarse_v3.cuh"
 #include "mol_coarse_l256.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -1037,17 +1033,9 @@ static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const Coar
   P.tile_map = out.tile_map;
   P.bc = bc;
   if (P.tile_end <= P.tile_begin) return MOL_OK;
-  // P_X * d == 256 (8x8x32, 8x4x64): the X-resident six-warpgroup kernel; wider item rows (8x4x128) do not fit TMEM next to
-  // two slots and keep the two-slot kernel with the item tile in shared memory
-  constexpr bool kV3 = (C::XCOLS == 256) && (MOL_COARSE_V3 != 0);
   static int sms = 0;  // (set once per process: the attribute call and the device query are not free on a 60 us search)
   if (sms == 0) {
-    if constexpr (kV3) {
-      MOL_CUDA(cudaFuncSetAttribute(v3::mol_coarse3_kernel<PX, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    v3::Cfg3<PX, DD>::SMEM_BYTES));
-    } else {
-      MOL_CUDA(cudaFuncSetAttribute(mol_coarse_kernel<PX, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    }
+    MOL_CUDA(cudaFuncSetAttribute(mol_coarse_kernel<PX, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     int dev = 0, n = 148;
     MOL_CUDA(cudaGetDevice(&dev));
     MOL_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
@@ -1057,11 +1045,7 @@ static int launch_coarse(const mol_shape_t& s, const mol_index_t& ix, const Coar
   MOL_CHECK_ARG(F < (1ll << 31), "coarse pass: tiles x queries = %lld does not fit 32 bits (use smaller query chunks)", (long long)F);
   int grid = (int)(F < sms ? F : sms);
   if (grid < 1) grid = 1;
-  if constexpr (kV3) {
-    v3::mol_coarse3_kernel<PX, DD><<<grid, v3::kThreads3, v3::Cfg3<PX, DD>::SMEM_BYTES, st>>>(tmX, tmGI, P);
-  } else {
-    mol_coarse_kernel<PX, DD><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmX, tmGI, P);
-  }
+  mol_coarse_kernel<PX, DD><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmX, tmGI, P);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
 }
