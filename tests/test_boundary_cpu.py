@@ -186,3 +186,32 @@ def test_get_top_k_module_names_match_the_reference():
             get_top_k_module(bad, model, items, ids)
     with pytest.raises(NotImplementedError):
         get_top_k_module("MoLNaiveFaissTopK5", model, items, ids)
+
+
+def test_round2_entry_points_host_side_contracts(monkeypatch):
+    """Host-only behaviour of the entry points added around the path: workspace sizes are pure host
+    calls that account for the streaming buffers, and argument errors come back as status codes before any CUDA work."""
+    from ctypes import byref, c_size_t
+
+    lib = _lib.load()
+    mol, _ = build_module(CFG_8x8x32, None, "cpu", seed=0)
+    shape = mol.mol_shape()
+    a, b, c = c_size_t(), c_size_t(), c_size_t()
+    # exclusion lists: the workspace grows with the list (internal over-fetch of the fp32 paths), never shrinks
+    assert lib.mol_search_workspace_bytes(byref(shape), 1_000_000, 64, 100, _lib.MODE_AUTO, byref(a)) == 0
+    assert lib.mol_search_excluding_workspace_bytes(byref(shape), 1_000_000, 64, 100, 211, _lib.MODE_AUTO, byref(b)) == 0
+    assert b.value >= a.value
+    assert lib.mol_search_excluding_workspace_bytes(byref(shape), 1_000_000, 64, 100, 0, _lib.MODE_AUTO, byref(c)) == 0
+    assert c.value == a.value
+    # MIPS: large corpora carry the streaming path's buffers on top of the (rows, N) matrix, and MOL_B200_DOTFILTER=0
+    # drops them again
+    assert lib.mol_mips_workspace_bytes(1_000_000, 64, 100, byref(a)) == 0
+    monkeypatch.setenv("MOL_B200_DOTFILTER", "0")
+    assert lib.mol_mips_workspace_bytes(1_000_000, 64, 100, byref(b)) == 0
+    monkeypatch.delenv("MOL_B200_DOTFILTER")
+    assert a.value > b.value >= 64 * 1_000_000 * 4
+    assert lib.mol_mips_workspace_bytes(10_000, 64, 100, byref(c)) == 0 and c.value < a.value
+    # argument errors: status + message, no CUDA call needed
+    assert lib.mol_mips_search_cached(None, None, None, 100, 64, 4, 101, None, None, None, None, 0, None) == _lib.MOL_ERR_RANGE
+    assert b"out of range" in lib.mol_last_error()
+    assert lib.mol_select_valid(None, None, None, 4, 10, 3, 20, None, None, None) == _lib.MOL_ERR_INVALID  # k' < k
