@@ -147,9 +147,9 @@ int launch_select_valid(const float* scores, const int64_t* ids, const int64_t* 
                         float* out_scores, int64_t* out_ids, const int32_t* query_flags, cudaStream_t st);
 
 // Index build on the tensor cores (mol_linear_x3_sm100.cu): tf32 x 3 split GEMMs with the l2-norm / silu / fp16-image
-// epilogues fused; `supported` looks at the shape, the corpus size and the alignment of raw_items
+// epilogues fused; `supported` looks at the shape, the corpus size and the alignment of raw_items / the biases
 // (MOL_B200_INDEX_X3=0 keeps the CUDA-core build).
-bool index_build_x3_supported(const mol_shape_t& s, const mol_index_t& ix);
+bool index_build_x3_supported(const mol_shape_t& s, const mol_weights_t& w, const mol_index_t& ix);
 size_t index_build_x3_workspace_bytes(const mol_shape_t& s, int64_t N);
 int index_build_x3(const mol_shape_t& s, const mol_weights_t& w, const mol_index_t& ix, void* workspace, cudaStream_t st);
 

@@ -722,7 +722,8 @@ int mol_index_build(const mol_shape_t* shape, const mol_weights_t* w, const mol_
     return MOL_ERR_WORKSPACE;
   }
   // tensor-core build: tf32 x 3 split GEMMs with fused l2-norm / silu / fp16-image epilogues (mol_linear_x3_sm100.cu)
-  if (N > 0 && index_build_x3_supported(*shape, *index)) return index_build_x3(*shape, *w, *index, workspace, st);
+  if (N > 0 && reinterpret_cast<uintptr_t>(workspace) % 256 == 0 && index_build_x3_supported(*shape, *w, *index))
+    return index_build_x3(*shape, *w, *index, workspace, st);
   float* tmp = static_cast<float*>(workspace);
   const int64_t Np = pad128(N);
   // zero the fp16 pad rows (and everything else) so the tensor-core pass can read whole tiles

@@ -488,7 +488,7 @@ int lx_layer(const float* A, int64_t M, int K, const float* W_hi, const float* W
 
 }  // namespace
 
-bool index_build_x3_supported(const mol_shape_t& s, const mol_index_t& ix) {
+bool index_build_x3_supported(const mol_shape_t& s, const mol_weights_t& w, const mol_index_t& ix) {
   const char* e = getenv("MOL_B200_INDEX_X3");
   if (e && atoi(e) == 0) return false;
   Dims D = dims_of(s);
@@ -497,7 +497,9 @@ bool index_build_x3_supported(const mol_shape_t& s, const mol_index_t& ix) {
   // every launch of the projection (a column chunk, or the remainder) must give each epilogue half whole l2-norm groups
   const int chunk = lx_chunk_cols(D.Dx, true);
   if (chunk < 2 * D.d || chunk % (2 * D.d) != 0 || (D.Px * D.d) % (2 * D.d) != 0) return false;
-  return ix.num_items >= 1024 && reinterpret_cast<uintptr_t>(ix.raw_items) % 16 == 0;
+  // TMA reads raw_items, the epilogues read the biases as float4
+  auto aligned16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  return ix.num_items >= 1024 && aligned16(ix.raw_items) && aligned16(w.x_b) && aligned16(w.gi_b1);
 }
 
 size_t index_build_x3_workspace_bytes(const mol_shape_t& s, int64_t N) {
