@@ -152,7 +152,8 @@ int mol_search_excluding(const mol_shape_t* shape, const mol_weights_t* w, const
 /* Counters of the LAST mol_search / mol_search_host call that used `workspace` (8 x int32, copied to host_stats; this
  * call synchronises the stream): [0] queries re-done by the exact fallback, [1] queries whose candidate filter
  * overflowed, [2] largest survivor count of a query, [3] 1 if the fused-filter strategy ran, [4] 1 if the tensor-core
- * path ran, [5] queries with fewer than K' survivors, [6] K', [7] survivor capacity per query. */
+ * path ran, [5] queries the first acceptance test refused and the second chance (every survivor of the fused filter
+ * rescored in fp32) accepted, [6] K', [7] survivor capacity per query. */
 int mol_search_stats(const void* workspace, int32_t* host_stats, mol_stream_t stream);
 
 /* Same call with HOST buffers for queries / user_ids / outputs (pinned memory recommended): copies

@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = (
 MOL_PACKED_ENTRY_BYTES = 16
 NUM_STATS = 8
 STAT_NAMES = ("fallback_queries", "filter_overflows", "max_survivors", "filter_strategy", "tensor_path",
-              "short_queries", "k_prime", "survivor_capacity")
+              "second_chance_queries", "k_prime", "survivor_capacity")
 
 
 class MolShape(ctypes.Structure):

@@ -59,12 +59,16 @@ int coarse_gi_image(const mol_shape_t& s, const float* gi_f32, uint16_t* gi_half
 // or when either overflow flag is set (operands did not fit fp16).
 // Filter strategy (cnt != nullptr): a query with fewer than kk survivors uses its threshold as the bound on every
 // item outside the candidate set; more survivors than `cap` (dropped candidates) flag the query.
-// stats (optional, 8 x int32, device): [0] += flagged queries, [1] += queries with more than `cap` survivors,
-// [2] = max survivors, [5] += queries with fewer than kk survivors.
+// second != 0: the second chance of the filter strategy - only queries whose flag is set are tested again, now with EVERY
+// survivor rescored (cand_scores / exact_scores = the (bc, cap) survivor buffers, kk = cap), so the bound on the items outside
+// the candidate set is the filter threshold itself.
+// stats (optional, 8 x int32, device): [0] += queries that go to the exact fallback (matrix strategy: first test; filter
+// strategy: second test), [1] += queries with more than `cap` survivors, [2] = max survivors, [5] += queries accepted by
+// the second chance.
 int coarse_safety_flags(const float* cand_scores, const float* exact_scores, const float* topk_scores,
                         int bc, int kk, int k, const int32_t* overflow_a, const int32_t* overflow_b,
                         const int32_t* cnt, const float* thr, int thr_stride, int cap, int32_t* flags,
-                        int32_t* stats, cudaStream_t st);
+                        int32_t* stats, int second, cudaStream_t st);
 // Appends every (score, item) of a (bc, n) matrix with !(score < thr[b]) to the per-query candidate buffers; column c
 // of the matrix is item (c / 128) * tile_stride * 128 + c % 128.
 int coarse_filter_matrix(const float* scores, int64_t n, int64_t ld, int bc, const float* thr, int thr_stride,

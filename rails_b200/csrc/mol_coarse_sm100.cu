@@ -1185,12 +1185,19 @@ __global__ void safety_flags_kernel(const float* __restrict__ cand, const float*
                                     const float* __restrict__ topk, int bc, int kk, int k,
                                     const int32_t* __restrict__ ovf_a, const int32_t* __restrict__ ovf_b,
                                     const int32_t* __restrict__ cnt, const float* __restrict__ thr, int thr_stride,
-                                    int cap, int32_t* __restrict__ flags, int32_t* __restrict__ stats) {
+                                    int cap, int32_t* __restrict__ flags, int32_t* __restrict__ stats, int second) {
   int b = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
   int lane = threadIdx.x % 32;
   if (b >= bc) return;
+  if (second && flags[b] == 0) return;  // second chance: only the queries the first test refused
+  // candidates that exist: the rest of a row is padding (first test) or unwritten buffer space (second chance)
+  int n = kk;
+  if (cnt) {
+    const int c = cnt[b];
+    n = c < kk ? (c < 0 ? 0 : c) : kk;
+  }
   float err = 0.f, cmin = CUDART_INF_F;
-  for (int j = lane; j < kk; j += 32) {
+  for (int j = lane; j < n; j += 32) {
     float c = cand[(int64_t)b * kk + j], e = exact[(int64_t)b * kk + j];
     if (c > -CUDART_INF_F && e > -CUDART_INF_F) {
       err = fmaxf(err, fabsf(c - e));
@@ -1211,28 +1218,34 @@ __global__ void safety_flags_kernel(const float* __restrict__ cand, const float*
       const int c = cnt[b];
       if (c > cap) bad = true;                              // survivors were dropped
       if (c <= kk) cmin = thr[(size_t)b * thr_stride];      // every survivor is a candidate: outsiders are below thr
-      if (stats) {
+      if (stats && !second) {
         if (c > cap) atomicAdd(stats + 1, 1);
-        if (c < kk) atomicAdd(stats + 5, 1);
         atomicMax(stats + 2, c);
       }
     }
-    // NaN-safe: anything but a provable "no" flags the query for the exact fallback
+    // NaN-safe: anything but a provable "no" flags the query
     const int f = (!bad && cmin + kSafetyErrFactor * err + kSafetyErrAbs < sk) ? 0 : 1;
     flags[b] = f;
-    if (stats && f) atomicAdd(stats + 0, 1);
+    if (stats) {
+      if (second) {
+        if (f) atomicAdd(stats + 0, 1);   // still refused: exact fallback
+        else atomicAdd(stats + 5, 1);     // accepted on the second chance
+      } else if (f && !cnt) {
+        atomicAdd(stats + 0, 1);          // matrix strategy: no second chance, straight to the exact fallback
+      }
+    }
   }
 }
 
 int coarse_safety_flags(const float* cand_scores, const float* exact_scores, const float* topk_scores,
                         int bc, int kk, int k, const int32_t* overflow_a, const int32_t* overflow_b,
                         const int32_t* cnt, const float* thr, int thr_stride, int cap, int32_t* flags,
-                        int32_t* stats, cudaStream_t st) {
+                        int32_t* stats, int second, cudaStream_t st) {
   if (bc == 0) return MOL_OK;
   int threads = bc * 32;
   safety_flags_kernel<<<(threads + 255) / 256, 256, 0, st>>>(cand_scores, exact_scores, topk_scores, bc, kk, k,
                                                              overflow_a, overflow_b, cnt, thr, thr_stride, cap,
-                                                             flags, stats);
+                                                             flags, stats, second);
   MOL_LAUNCH_CHECK();
   return MOL_OK;
 }

@@ -122,13 +122,17 @@ def test_acceptance_check_10k_queries_no_miss():
     assert miss == 0
 
 
-def test_dense_scores_tiny_gap_falls_back_and_stays_exact(force_filter):
-    """Adversarial for the acceptance test: the corpus is a few hundred prototypes, each repeated ~hundreds of times with
-    perturbations far below the coarse pass's resolution, so the gap between rank k and rank K' is ~1e-5 while the coarse
-    error is ~1e-2.  The check must refuse the coarse candidate set (flag the queries) and the exact fallback must return
-    the exact answer."""
+@pytest.mark.parametrize("P,reps,expect", [(256, 400, "second_chance"), (64, 5000, "exact_fallback")])
+def test_dense_scores_tiny_gap_falls_back_and_stays_exact(P, reps, expect, force_filter):
+    """Adversarial for the acceptance test: the corpus is a few hundred prototypes, each repeated hundreds / thousands of times
+    with perturbations far below the coarse pass's resolution, so the gap between rank k and rank K' is ~1e-5 while the
+    coarse error is ~1e-2.  The first test must refuse the coarse top-K'.  With 400 copies per prototype the second chance
+    (every survivor of the fused filter rescored: the copies of the best two or three prototypes) proves the answer; with
+    5000 copies the filter threshold falls INSIDE the best prototype's cluster (the ~1100 survivors are the copies with the
+    largest coarse scores, the other ~3900 copies tie with them exactly and lie just below the threshold), the second test
+    must refuse as well and the exact fallback must return the exact answer."""
     cfg = CFG_8x8x32
-    P, reps, B, k = 256, 400, 6, 100
+    B, k = 6, 100
     mol, _ = build_module(cfg, None, DEV, seed=43)
     proto, _, q, _ = synthetic_inputs(cfg, P, B, 43, DEV)
     g = torch.Generator(device=DEV).manual_seed(7)
@@ -139,7 +143,11 @@ def test_dense_scores_tiny_gap_falls_back_and_stays_exact(force_filter):
     s, i = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=_lib.MODE_AUTO)(q, k=k)
     st = _stats(mol)
     s_ex, i_ex = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=_lib.MODE_EXACT)(q, k=k)
-    assert st["tensor_path"] == 1 and st["fallback_queries"] == B, st
+    assert st["tensor_path"] == 1 and st["fallback_queries"] + st["second_chance_queries"] == B, st
+    if expect == "second_chance":
+        assert st["second_chance_queries"] == B, st
+    else:
+        assert st["fallback_queries"] == B, st
     assert torch.equal(s, s_ex)
     # near-duplicate items tie EXACTLY in fp32, and which members of a tie at rank k a select keeps is unspecified (as with
     # torch.topk): ids are checked against the full exact score matrix instead of against the other run's choice
@@ -307,3 +315,26 @@ def test_small_searches_take_the_exact_kernel_in_auto_mode(monkeypatch):
     assert torch.equal(out["switch"][1], out["tensor"][1]) and torch.equal(out["switch"][0], out["tensor"][0])
     r = O.compare_top_k(out["switch"][0][:1], out["switch"][1][:1], g["ref_scores"][:1], g["item_ids"], g["k"], 1e-3, 1e-4)
     assert r["ok"] == 1.0, r
+
+
+def test_second_chance_rescoring_all_survivors_equals_exact(force_filter, monkeypatch):
+    """Filter strategy: a query the first acceptance test refuses gets EVERY survivor of the fused filter rescored in fp32
+    before the full exact pass is considered.  With the first test forced to refuse everything
+    (MOL_B200_FORCE_SECOND_CHANCE) all queries must be served by the second chance (no exact fallback) and equal the
+    exact mode."""
+    cfg = CFG_8x8x32
+    N, B, k = 300_000, 24, 100
+    mol, _ = build_module(cfg, None, DEV, seed=61)
+    items, ids, q, _ = synthetic_inputs(cfg, N, B, 61, DEV)
+    monkeypatch.setenv("MOL_B200_FORCE_SECOND_CHANCE", "1")
+    s, i = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=_lib.MODE_AUTO)(q, k=k)
+    st = _stats(mol)
+    monkeypatch.delenv("MOL_B200_FORCE_SECOND_CHANCE")
+    s_ex, i_ex = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=_lib.MODE_EXACT)(q, k=k)
+    assert st["filter_strategy"] == 1 and st["second_chance_queries"] == B and st["fallback_queries"] == 0, st
+    assert torch.equal(i, i_ex) and torch.equal(s, s_ex)
+    # and without the hook nothing is refused on this workload
+    s2, i2 = MoLBruteForceTopK(mol, items.unsqueeze(0), ids.unsqueeze(0), mode=_lib.MODE_AUTO)(q, k=k)
+    st2 = _stats(mol)
+    assert st2["second_chance_queries"] == 0 and st2["fallback_queries"] == 0, st2
+    assert torch.equal(i2, i_ex) and torch.equal(s2, s_ex)
